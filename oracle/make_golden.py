@@ -1,0 +1,150 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference — TEST INFRASTRUCTURE.
+
+Run in the authoring container (where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+The reference's own offline_tango (tango.py:252), intern_filter
+(internal_formulas.py:31), tf_mask (dnn/utils.py:44), vad_oracle_batch
+(sigproc_utils.py:12), spatial_correlation_matrix (internal_formulas.py:84),
+concatenate_signals / get_z_for_mask / reshape_mask (tango.py:142-240) are imported
+through oracle/ref_shim.py and executed on seeded synthetic inputs
+(disco_b200/synth.py).  Only librosa's STFT is restated (oracle/librosa_np.py).
+Inputs are regenerated from their seeds by the tests; a checksum guards the generator.
+"""
+import hashlib
+import os
+
+import numpy as np
+
+from disco_b200.synth import make_utterance
+from oracle import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TANGO_CASES = {
+    # name: (seed, channels per node, L, vads, mask_for_z, outputs kept)
+    "tango_k1c2_cfg1": (0, [2], 64000, ("irm1", "irm1"), "local", ("yf", "z_y")),
+    "tango_k2c3_local": (1, [3, 3], 8192, ("irm1", "irm1"), "local", None),
+    "tango_k3_ragged_local": (2, [2, 3, 2], 6000, ("irm1", "irm1"), "local", ("yf", "z_y", "zn", "sf")),
+    "tango_k3c2_distant": (3, [2, 2, 2], 6000, ("irm1", "irm1"), "distant", ("yf", "z_y", "nf")),
+    "tango_k2c4_irm2_iam1": (4, [4, 4], 5000, ("irm2", "iam1"), "local", ("yf", "z_y", "masks_z", "mask_w")),
+    "tango_k2c2_ibm1": (5, [2, 2], 5000, ("ibm1", "ibm1"), "local", ("yf", "z_y", "masks_z")),
+    "tango_k2c2_ivad": (6, [2, 2], 8192, ("ivad", "ivad"), "local", ("yf", "z_y", "masks_z")),
+    # mask_for_z=None raises TypeError in the reference (tango.py:343 `in None`): no fixture.
+    "tango_k2c2_previous": (7, [2, 2], 5000, ("irm1", "irm1"), "previous", ("yf", "z_y")),
+    "tango_k2c2_compressed": (8, [2, 2], 5000, ("irm1", "irm1"), "compressed", ("yf", "z_y")),
+    "tango_k2c2_oracle_refs": (9, [2, 2], 5000, ("irm1", "irm1"), "use_oracle_refs", ("yf", "z_y")),
+    "tango_k2c2_oracle_zs": (10, [2, 2], 5000, ("irm1", "irm1"), "use_oracle_zs", ("yf", "z_y")),
+}
+NAMES = ("yf", "sf", "nf", "z_y", "z_s", "z_n", "zn", "masks_z", "mask_w")
+
+
+def case_inputs(seed, chans, length, vads=("irm1", "irm1")):
+    """[node][channel] lists as the reference expects (ragged channel counts allowed)."""
+    K, cmax = len(chans), max(chans)
+    y, s, n = make_utterance(seed, K, cmax, length, gate_period=2000 if "ivad" in vads else 0)
+    pick = lambda a: [[a[k, c] for c in range(chans[k])] for k in range(K)]
+    return pick(y), pick(s), pick(n)
+
+
+def digest(y):
+    h = hashlib.sha256()
+    for node in y:
+        for ch in node:
+            h.update(np.ascontiguousarray(ch).tobytes())
+    return h.hexdigest()
+
+
+def rand_hpd(rng, d, rank=None, dtype=np.complex64):
+    r = d + 2 if rank is None else rank
+    a = rng.standard_normal((d, r)) + 1j * rng.standard_normal((d, r))
+    return (a @ a.conj().T / r).astype(dtype)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+
+    for name, (seed, chans, length, vads, mfz, keep) in TANGO_CASES.items():
+        y, s, n = case_inputs(seed, chans, length, vads)
+        res = ref_shim.run_offline_tango(y, s, n, vads=vads, mask_for_z=mfz)
+        blob = {"input_sha256": np.array(digest(y))}
+        for nm, val in zip(NAMES, res):
+            if keep is not None and nm not in keep:
+                continue
+            for k, arr in enumerate(val):
+                arr = np.asarray(arr)
+                if np.iscomplexobj(arr):
+                    arr = arr.astype(np.complex64)
+                elif arr.dtype == np.float64 and nm.startswith("mask"):
+                    arr = arr.astype(np.float32) if np.array_equal(arr.astype(np.float32), arr) else arr
+                blob["%s_%d" % (nm, k)] = arr
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
+        print(name, {k: v.shape for k, v in blob.items() if k.endswith("_0")})
+
+    # ---- intern_filter known answers (complex64 and complex128 inputs, all three types)
+    rng = np.random.default_rng(42)
+    blob = {}
+    i = 0
+    for d in (2, 3, 4, 7, 9):
+        for dt in (np.complex64, np.complex128):
+            Rxx = rand_hpd(rng, d, rank=None, dtype=dt) + 4 * rand_hpd(rng, d, rank=1, dtype=dt)
+            Rnn = rand_hpd(rng, d, dtype=dt)
+            for typ, rank, mu in (("gevd", 1, 1), ("gevd", 2, 1), ("gevd", 1, 3.5), ("gevd", "full", 1),
+                                  ("mwf", None, 1), ("r1-mwf", None, 1), ("r1-mwf", None, 2.0)):
+                if rank is None:
+                    W, (t1, _) = ref.intern_filter(Rxx, Rnn, mu=mu, type=typ)
+                else:
+                    if typ == "gevd" and rank != "full" and rank > d:
+                        continue
+                    W, (t1, _) = ref.intern_filter(Rxx, Rnn, mu=mu, type=typ, rank=rank)
+                blob["Rxx_%d" % i], blob["Rnn_%d" % i] = Rxx, Rnn
+                blob["W_%d" % i], blob["t1_%d" % i] = np.asarray(W), np.asarray(t1)
+                blob["cfg_%d" % i] = np.array("%s|%s|%s" % (typ, rank, mu))
+                i += 1
+    blob["count"] = np.array(i)
+    np.savez_compressed(os.path.join(OUT, "intern_filter_kat.npz"), **blob)
+    print("intern_filter KATs:", i)
+
+    # ---- masks, VAD, recursive SCM, list helpers
+    rng = np.random.default_rng(7)
+    sa = (rng.standard_normal((17, 23)) + 1j * rng.standard_normal((17, 23))).astype(np.complex64)
+    na = (rng.standard_normal((17, 23)) + 1j * rng.standard_normal((17, 23))).astype(np.complex64)
+    na[3, 4] = 0
+    sa[5, 6] = 0
+    blob = {"s": sa, "n": na}
+    for typ in ("irm1", "irm2", "ibm1", "ibm2", "iam1", "iam2"):
+        blob["dnn_" + typ] = ref.tf_mask(sa, na, type=typ)
+        blob["sig_" + typ] = ref.tf_mask_sigproc(sa, na, type=typ)
+    blob["dnn_ibm1_thr3"] = ref.tf_mask(sa, na, type="ibm1", bin_thr=3)
+    x = (0.1 * rng.standard_normal(5000) * (np.arange(5000) % 2000 < 900)).astype(np.float32)
+    blob["vad_x"] = x
+    blob["vad_default"] = ref.vad_oracle_batch(x)
+    blob["vad_256_128"] = ref.vad_oracle_batch(x, win_len=256, win_hop=128, thr=0.01, rat=4)
+    R0 = rand_hpd(rng, 4, dtype=np.complex128)
+    xv = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+    blob["scm_R0"], blob["scm_x"] = R0, xv
+    blob["scm_plain"] = ref.spatial_correlation_matrix(R0, xv)
+    blob["scm_masked"] = ref.spatial_correlation_matrix(R0, xv, lambda_cor=0.9, M=0.3)
+    ys = [(rng.standard_normal((2, 5, 6)) + 0j).astype(np.complex64) for _ in range(3)]
+    zs = [(rng.standard_normal((5, 6)) * 1j).astype(np.complex64) for _ in range(3)]
+    zn_ = [(rng.standard_normal((5, 6)) + 0j).astype(np.complex64) for _ in range(3)]
+    mk = rng.uniform(size=(5, 6)).astype(np.float32)
+    blob["cat_y"], blob["cat_z"], blob["cat_zn"], blob["cat_m"] = np.array(ys), np.array(zs), np.array(zn_), mk
+    for k in range(3):
+        blob["cat_%d" % k] = ref.concatenate_signals(ys, zs, k)
+        blob["catm_%d" % k] = ref.concatenate_signals(ys, zs, k, mk)
+        blob["zmask_zs_%d" % k] = ref.get_z_for_mask(zs, zn_, k, 3, "zs_hat")
+        blob["zmask_zn_%d" % k] = ref.get_z_for_mask(zs, zn_, k, 3, "zn_hat")
+        blob["zmask_both_%d" % k] = ref.get_z_for_mask(zs, zn_, k, 3, ["zs_hat", "zn_hat"])
+    mstack = rng.uniform(size=(9, 15, 11)).astype(np.float32)
+    blob["reshape_in"] = mstack
+    blob["reshape_last"] = ref.reshape_mask(mstack, "last")
+    blob["reshape_mid"] = ref.reshape_mask(mstack, "mid")
+    np.savez_compressed(os.path.join(OUT, "helpers_kat.npz"), **blob)
+    print("helpers KATs written")
+
+
+if __name__ == "__main__":
+    main()
