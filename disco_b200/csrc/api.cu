@@ -1,0 +1,309 @@
+// C ABI of libdisco_b200.so (declared in include/disco_b200.h): argument checking, per-device
+// constant tables, launch-geometry choices.  No torch types cross this boundary.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/disco_b200.h"
+#include "kernels.h"
+
+using namespace disco;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CU(expr, where)                                  \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return cuda_fail(_e, where); \
+    } while (0)
+
+bool valid_nfft(int n) { return n == 256 || n == 512 || n == 1024; }
+
+struct Tables {
+    float2* twiddle = nullptr;   // [N/32][32] W_N^(l k1)
+    float* win_half = nullptr;   // 0.5 * periodic Hann (forward: two-for-one split needs the 1/2)
+    float* win = nullptr;        // periodic Hann
+};
+std::mutex g_mu;
+std::map<std::pair<int, int>, Tables> g_tables;  // (device, n_fft)
+
+// Build (once per device and n_fft) the twiddle and window tables, computed in double on the host.
+int get_tables(int n_fft, Tables* out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, n_fft);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) {
+        *out = it->second;
+        return 0;
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    (void)cs;
+    const int RA = n_fft / 32;
+    std::vector<float2> tw(n_fft);
+    std::vector<float> wh(n_fft), w(n_fft);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k1 = 0; k1 < RA; ++k1)
+        for (int l = 0; l < 32; ++l) {
+            const double ang = -two_pi * (double)(l * k1) / (double)n_fft;
+            tw[k1 * 32 + l] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int n = 0; n < n_fft; ++n) {
+        const double h = 0.5 - 0.5 * cos(two_pi * (double)n / (double)n_fft);
+        w[n] = (float)h;
+        wh[n] = (float)(0.5 * h);
+    }
+    Tables t;
+    CU(cudaMalloc(&t.twiddle, n_fft * sizeof(float2)), "cudaMalloc tables");
+    CU(cudaMalloc(&t.win_half, n_fft * sizeof(float)), "cudaMalloc tables");
+    CU(cudaMalloc(&t.win, n_fft * sizeof(float)), "cudaMalloc tables");
+    CU(cudaMemcpy(t.twiddle, tw.data(), n_fft * sizeof(float2), cudaMemcpyHostToDevice), "cudaMemcpy tables");
+    CU(cudaMemcpy(t.win_half, wh.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy tables");
+    CU(cudaMemcpy(t.win, w.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy tables");
+    g_tables[key] = t;
+    *out = t;
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+// Split T frames of every group into chunks (multiples of the tile) so the grid fills the GPU.
+void choose_chunks(int n_grp, int T, int tile, int* n_chunk, int* fpc) {
+    const int want = sm_count() * 2;
+    int chunks = 1;
+    while (n_grp * chunks < want && (T + chunks - 1) / chunks > 4 * tile) chunks *= 2;
+    int f = ((T + chunks - 1) / chunks + tile - 1) / tile * tile;
+    *fpc = f;
+    *n_chunk = (T + f - 1) / f;
+}
+
+int stft_common(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_sig,
+                int C, int length, int n_fft, void* workspace, size_t workspace_bytes, bool scm, void* stream) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (n_sig <= 0 || length <= n_fft / 2)
+        return fail(DISCO_ERR_INVALID, "need n_sig > 0 and length > n_fft/2 (reflect padding)");
+    if (C < 1 || C > 4) return fail(DISCO_ERR_UNSUPPORTED, "fused STFT+SCM supports 1..4 channels per group");
+    if (!x || !Y) return fail(DISCO_ERR_INVALID, "null pointer");
+    Tables tb;
+    int rc = get_tables(n_fft, &tb);
+    if (rc) return rc;
+    const int T = disco_n_frames(length, n_fft);
+    const int n_grp = (n_sig + C - 1) / C;
+    StftArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x;
+    a.mask = mask;
+    a.Y = (float2*)Y;
+    a.part = (float*)workspace;
+    a.twiddle = tb.twiddle;
+    a.window = tb.win_half;
+    a.n_sig = n_sig;
+    a.L = length;
+    a.T = T;
+    a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
+    a.use_tma = (length % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    choose_chunks(n_grp, T, stft_tile_frames(C), &a.n_chunk, &a.frames_per_chunk);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (scm) {
+        if (!mask || !Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
+        const size_t need = disco_stft_scm_workspace(n_grp, C, length, n_fft);
+        if (!workspace || workspace_bytes < need) return fail(DISCO_ERR_WORKSPACE, "workspace too small");
+    }
+    CU(launch_stft_scm(a, n_fft, C, n_grp, scm, st), "stft_scm launch");
+    if (scm)
+        CU(launch_scm_finalize(a.part, (float2*)Rss, (float2*)Rnn, n_grp, a.n_chunk, C, n_fft / 2 + 1, T, st),
+           "scm_finalize launch");
+    return 0;
+}
+
+}  // namespace
+
+
+extern "C" {
+
+int disco_abi_version(void) { return DISCO_ABI_VERSION; }
+const char* disco_last_error(void) { return g_err.c_str(); }
+
+int disco_n_frames(int length, int n_fft) { return 1 + length / (n_fft / 2); }
+
+int disco_init(int n_fft) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    Tables tb;
+    return get_tables(n_fft, &tb);
+}
+
+int disco_stft(const float* x, void* Y, int n_sig, int length, int n_fft, void* stream) {
+    // plain STFT: signals are grouped by 4 only to share a CTA's tile; groups are independent
+    const int C = n_sig >= 4 ? 4 : n_sig;
+    return stft_common(x, nullptr, 0, Y, nullptr, nullptr, n_sig, C, length, n_fft, nullptr, 0, false, stream);
+}
+
+size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft) {
+    if (!valid_nfft(n_fft) || C < 1 || n_grp < 1) return 0;
+    const int T = disco_n_frames(length, n_fft);
+    int n_chunk, fpc;
+    choose_chunks(n_grp, T, stft_tile_frames(C > 4 ? 4 : C), &n_chunk, &fpc);
+    return (size_t)n_grp * n_chunk * 2 * C * C * (n_fft / 2 + 1) * sizeof(float);
+}
+
+int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_grp,
+                   int C, int length, int n_fft, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_grp <= 0) return fail(DISCO_ERR_INVALID, "n_grp must be positive");
+    return stft_common(x, mask, mask_layout, Y, Rss, Rnn, n_grp * C, C, length, n_fft, workspace, workspace_bytes,
+                       true, stream);
+}
+
+int disco_tf_mask(const void* S, const void* N, float* M, size_t n_elem, int kind, int power, float bin_thr_db,
+                  void* stream) {
+    if (kind < 0 || kind > 2) return fail(DISCO_ERR_INVALID, "unknown mask kind");
+    if (power < 0 || power > 9) return fail(DISCO_ERR_INVALID, "mask power must be a single digit");
+    if (!S || !N || !M) return fail(DISCO_ERR_INVALID, "null pointer");
+    const float thr = powf(10.f, bin_thr_db / 10.f);  // math_utils.db2lin
+    CU(launch_tf_mask((const float2*)S, (const float2*)N, M, n_elem, kind, power, thr, (cudaStream_t)stream),
+       "tf_mask launch");
+    return 0;
+}
+
+static int make_cat(CatArgs* c, const void* Y, const void* Z, int n_utt, int K, int C, int T, int n_fft,
+                    const int* node_sel, int n_sel) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (n_utt <= 0 || K < 1 || C < 1 || T < 1) return fail(DISCO_ERR_INVALID, "bad sizes");
+    if (C + K - 1 > 16) return fail(DISCO_ERR_UNSUPPORTED, "C + K - 1 must be <= 16");
+    if (!Y || (K > 1 && !Z)) return fail(DISCO_ERR_INVALID, "null pointer");
+    c->Y = (const float2*)Y;
+    c->Z = (const float2*)Z;
+    c->C = C;
+    c->K = K;
+    c->T = T;
+    c->F = n_fft / 2 + 1;
+    if (K > 16) return fail(DISCO_ERR_UNSUPPORTED, "at most 16 nodes");
+    if (node_sel) {
+        if (n_sel < 1 || n_sel > K) return fail(DISCO_ERR_INVALID, "bad node selection");
+        for (int i = 0; i < n_sel; ++i) {
+            if (node_sel[i] < 0 || node_sel[i] >= K || (i > 0 && node_sel[i] <= node_sel[i - 1]))
+                return fail(DISCO_ERR_INVALID, "node selection must be ascending node indices");
+            c->sel[i] = node_sel[i];
+        }
+        c->n_sel = n_sel;
+    } else {
+        c->n_sel = K;
+        for (int i = 0; i < K; ++i) c->sel[i] = i;
+    }
+    c->n_grp = n_utt * c->n_sel;
+    return 0;
+}
+
+int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_layout, void* Rss, void* Rnn,
+                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, void* stream) {
+    ScmArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    if (rc) return rc;
+    if (!Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
+    a.mask = mask;
+    a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
+    a.Rss = (float2*)Rss;
+    a.Rnn = (float2*)Rnn;
+    CU(launch_masked_scm(a, (cudaStream_t)stream), "masked_scm launch");
+    return 0;
+}
+
+int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
+                    int rank, double mu, void* stream) {
+    if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");
+    if (D < 1 || D > 16) return fail(DISCO_ERR_UNSUPPORTED, "D must be in 1..16");
+    if (n_mat < 0 || !Rss || !Rnn || !W) return fail(DISCO_ERR_INVALID, "bad arguments");
+    SolveArgs a;
+    a.Rss = (const float2*)Rss;
+    a.Rnn = (const float2*)Rnn;
+    a.W = (float2*)W;
+    a.T1 = (float2*)T1;
+    a.n_mat = n_mat;
+    a.D = D;
+    a.type = filter_type;
+    a.rank = rank;
+    a.mu = mu;
+    CU(launch_mwf_solve(a, (cudaStream_t)stream), "mwf_solve launch");
+    return 0;
+}
+
+int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
+                     int out_layout, int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel,
+                     void* stream) {
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    if (rc) return rc;
+    if (!W || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (ref < 0 || ref >= C + K - 1) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    a.W = (const float2*)W;
+    a.conj_w = conj_w;
+    a.out = (float2*)out;
+    a.resid = (float2*)resid;
+    a.ref = ref;
+    a.out_ft = (out_layout == DISCO_LAYOUT_FT);
+    CU(launch_filter_sum(a, (cudaStream_t)stream), "filter_sum launch");
+    return 0;
+}
+
+int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft, void* stream) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (n_sig <= 0 || T < 1 || length < 1 || !Y || !x) return fail(DISCO_ERR_INVALID, "bad arguments");
+    Tables tb;
+    int rc = get_tables(n_fft, &tb);
+    if (rc) return rc;
+    IstftArgs a;
+    a.Y = (const float2*)Y;
+    a.x = x;
+    a.twiddle = tb.twiddle;
+    a.window = tb.win;
+    a.n_sig = n_sig;
+    a.L = length;
+    a.T = T;
+    CU(launch_istft(a, n_fft, (cudaStream_t)stream), "istft launch");
+    return 0;
+}
+
+int disco_transpose_c64(const void* in, void* out, int batch, int rows, int cols, void* stream) {
+    if (!in || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    CU(launch_transpose_c64((const float2*)in, (float2*)out, batch, rows, cols, (cudaStream_t)stream),
+       "transpose launch");
+    return 0;
+}
+int disco_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream) {
+    if (!in || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    CU(launch_transpose_f32(in, out, batch, rows, cols, (cudaStream_t)stream), "transpose launch");
+    return 0;
+}
+int disco_apply_mask(const void* in, const float* m, void* out, size_t n_elem, int one_minus, void* stream) {
+    if (!in || !m || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    CU(launch_apply_mask((const float2*)in, m, (float2*)out, n_elem, one_minus, (cudaStream_t)stream),
+       "apply_mask launch");
+    return 0;
+}
+
+}  // extern "C"

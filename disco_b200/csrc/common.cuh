@@ -1,0 +1,65 @@
+// Shared device helpers for the disco_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DISCO_DEV __device__ __forceinline__
+
+namespace disco {
+
+// ---------------------------------------------------------------- complex helpers (float2)
+DISCO_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DISCO_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+DISCO_DEV float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+DISCO_DEV float2 cmulc(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+DISCO_DEV float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+DISCO_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// acc += s * a   (s real)
+DISCO_DEV float2 cfma_r(float s, float2 a, float2 acc) { return __ffma2_rn(make_float2(s, s), a, acc); }
+
+// ---------------------------------------------------------------- shared-memory / TMA plumbing
+DISCO_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DISCO_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+DISCO_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+DISCO_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion on an mbarrier.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+DISCO_DEV void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+DISCO_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DISCO_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// streaming (evict-first) 8-byte global store: outputs are written once and not re-read by this kernel
+DISCO_DEV void st_stream(float2* p, float2 v) { __stcs(p, v); }
+DISCO_DEV float ld_stream(const float* p) { return __ldcs(p); }
+DISCO_DEV float2 ld_stream(const float2* p) { return __ldcs(p); }
+
+}  // namespace disco

@@ -1,0 +1,90 @@
+// Internal launcher interface between the kernel translation units and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace disco {
+
+struct StftArgs {
+    const float* x;         // [n_sig][L] float32 time signals (n_sig = n_grp * C, last group may be short)
+    const float* mask;      // SCM only: [n_grp][T][F] (mask_ft = 0) or [n_grp][F][T] (mask_ft = 1)
+    float2* Y;              // [n_sig][T][F] complex64, frame-major
+    float* part;            // SCM only: [n_grp][n_chunk][2 C^2][F] partial sums
+    const float2* twiddle;  // [N/32][32]: W_N^(l*k1)
+    const float* window;    // [N]: 0.5 * periodic Hann
+    int n_sig, L, T;
+    int n_chunk, frames_per_chunk;
+    int mask_ft;
+    int use_tma;
+};
+
+cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_grp, bool scm, cudaStream_t st);
+cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int n_chunk, int C,
+                                int F, int T, cudaStream_t st);
+int stft_tile_frames(int C);
+
+// Step-2 style input: group g = (utterance b, node k) sees D = C + K - 1 channels:
+// its own C microphone spectra, then the compressed signals z of the other nodes in node
+// order (reference concatenate_signals, tango.py:142-155).
+// Ragged arrays (nodes with different microphone counts) are handled by launching once per
+// channel count on the subset `sel` of nodes that have C microphones: group g = (b, sel[g % n_sel]).
+struct CatArgs {
+    const float2* Y;   // [n_grp][C][T][F]
+    const float2* Z;   // [n_utt][K][T][F]   (may be null when K == 1)
+    int C, K, T, F;
+    int n_grp;         // = n_utt * n_sel
+    int n_sel;         // nodes covered by this launch (K when all nodes have C microphones)
+    int sel[16];       // their node indices, ascending
+};
+
+struct ScmArgs {
+    CatArgs in;
+    const float* mask;   // [n_grp][T][F] or [n_grp][F][T]; null = all ones (plain SCM into Rss, Rnn = 0)
+    int mask_ft;
+    float2* Rss;         // [n_grp][F][D][D]
+    float2* Rnn;
+};
+cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st);
+
+struct SolveArgs {
+    const float2* Rss;   // [n_mat][D][D]
+    const float2* Rnn;
+    float2* W;           // [n_mat][D]
+    float2* T1;          // [n_mat][D] (may be null)
+    int n_mat, D;
+    int type;            // 0 gevd, 1 r1-mwf, 2 mwf
+    int rank;            // gevd: number of generalised eigenpairs kept; <= 0 or >= D means full
+    double mu;
+};
+cudaError_t launch_mwf_solve(const SolveArgs& a, cudaStream_t st);
+
+struct FilterArgs {
+    CatArgs in;
+    const float2* W;     // [n_grp][F][D]
+    int conj_w;          // 1: w^H x (reference np.inner(conj(w), x)); 0: w^T x (reference np.inner(t1, x))
+    float2* out;         // [n_grp][T][F] (out_ft = 0) or [n_grp][F][T] (out_ft = 1)
+    float2* resid;       // optional: in[ref] - out, same layout as out (reference zn, tango.py:376)
+    int ref;             // reference channel for resid
+    int out_ft;
+};
+cudaError_t launch_filter_sum(const FilterArgs& a, cudaStream_t st);
+
+struct IstftArgs {
+    const float2* Y;     // [n_sig][T][F] frame-major complex64
+    float* x;            // [n_sig][L]
+    const float2* twiddle;
+    const float* window; // [N] periodic Hann (unscaled)
+    int n_sig, L, T;
+};
+cudaError_t launch_istft(const IstftArgs& a, int n_fft, cudaStream_t st);
+
+cudaError_t launch_tf_mask(const float2* S, const float2* Nn, float* M, size_t n, int kind, int power,
+                           float thr_lin, cudaStream_t st);
+// out[b][c][r] = in[b][r][c]
+cudaError_t launch_transpose_c64(const float2* in, float2* out, int batch, int rows, int cols, cudaStream_t st);
+cudaError_t launch_transpose_f32(const float* in, float* out, int batch, int rows, int cols, cudaStream_t st);
+// out = m * in or (1 - m) * in, elementwise over [n][T*F]; mask broadcast per group
+cudaError_t launch_apply_mask(const float2* in, const float* m, float2* out, size_t n, int one_minus,
+                              cudaStream_t st);
+
+}  // namespace disco

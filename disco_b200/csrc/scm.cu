@@ -1,0 +1,220 @@
+// Mask-weighted spatial covariance matrices of D = C + K - 1 channel spectra that are already
+// in HBM (step 2 of Tango: own microphones + compressed signals of the other nodes).
+//
+// Replaces the second triple loop of the reference (tango.py:431-440):
+//   in_to_phi_s = concat(m * Y_k, m * z_others), in_to_phi_n = concat((1-m) * Y_k, (1-m) * z_others)
+//   R_ss[f] = mean_t a a^H,  R_nn[f] = mean_t b b^H          (np.outer convention: R[i][j] = a_i conj(a_j))
+// i.e. weights m^2 and (1-m)^2 on ONE outer product y y^H per (f, t), never materialising a, b.
+//
+// Data are frame-major ([.., T, F], F contiguous), so a warp covers 32 consecutive bins of one
+// frame with coalesced 8-byte loads and every thread owns one bin: no shuffles are needed, the
+// time reduction is a register accumulation.  A CTA owns (group, 32-bin block) for ALL frames:
+//   threads = 32 bins x NPART pair-partitions x TW time-ways
+// The D(D+1)/2 Hermitian pairs are dealt round-robin to NPART warps-uniform partitions so the
+// accumulators fit in registers for D up to 16; the TW time-ways are reduced through shared
+// memory at the end (fixed order -> deterministic), then scaled by 1/T and written with their
+// conjugate mirrors.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace disco {
+
+template <int D>
+struct ScmGeom {
+    static constexpr int NPAIR = D * (D + 1) / 2;
+    static constexpr int NPART = D <= 4 ? 1 : (D <= 6 ? 2 : (D <= 9 ? 4 : 8));
+    static constexpr int NPP = (NPAIR + NPART - 1) / NPART;  // pairs per partition
+    static constexpr int TW = 8 / NPART;
+    static constexpr int THREADS = 256;
+};
+
+// pair index -> (i, j), i <= j, row-major over the upper triangle (compile-time)
+template <int D>
+__host__ __device__ constexpr int pair_i(int p) {
+    int i = 0, n = D;
+    while (p >= n) {
+        p -= n;
+        --n;
+        ++i;
+    }
+    return i;
+}
+template <int D>
+__host__ __device__ constexpr int pair_j(int p) {
+    int i = 0, n = D;
+    while (p >= n) {
+        p -= n;
+        --n;
+        ++i;
+    }
+    return i + p;
+}
+
+DISCO_DEV const float2* cat_channel(const CatArgs& in, int grp, int d) {
+    if (d < in.C) return in.Y + ((size_t)grp * in.C + d) * in.T * in.F;
+    const int b = grp / in.n_sel, k = in.sel[grp % in.n_sel];
+    int j = d - in.C;
+    if (j >= k) ++j;  // skip own compressed signal (tango.py:153-155)
+    return in.Z + ((size_t)b * in.K + j) * in.T * in.F;
+}
+
+// compile-time recursion over the pairs of one partition: (i, j) are constants, so y[] and the
+// accumulators stay in registers
+template <int D, int PART, int Q>
+struct PairAcc {
+    using G = ScmGeom<D>;
+    static DISCO_DEV void run(const float2 (&y)[D], float wa, float wb, float2 (&ps)[G::NPP], float2 (&pn)[G::NPP]) {
+        if constexpr (Q < G::NPP) {
+            constexpr int pidx = Q * G::NPART + PART;
+            if constexpr (pidx < G::NPAIR) {
+                constexpr int i = pair_i<D>(pidx), j = pair_j<D>(pidx);
+                const float2 op = cmulc(y[i], y[j]);
+                ps[Q] = cfma_r(wa, op, ps[Q]);
+                pn[Q] = cfma_r(wb, op, pn[Q]);
+            }
+            PairAcc<D, PART, Q + 1>::run(y, wa, wb, ps, pn);
+        }
+    }
+};
+
+template <int D, int PART>
+DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int tw,
+                              float2 (&ps)[ScmGeom<D>::NPP], float2 (&pn)[ScmGeom<D>::NPP]) {
+    using G = ScmGeom<D>;
+    const int T = a.in.T, F = a.in.F;
+    const float2* ch[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) ch[d] = cat_channel(a.in, grp, d) + f;
+    const float* mrow = a.mask ? (a.mask_ft ? a.mask + ((size_t)grp * F + f) * T : a.mask + (size_t)grp * T * F + f)
+                               : nullptr;
+    const size_t mstride = a.mask_ft ? 1 : F;
+    for (int t = tw; t < T; t += G::TW) {
+        float2 y[D];
+        float m = 1.f;
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = ch[d][(size_t)t * F];
+            if (mrow) m = mrow[(size_t)t * mstride];
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = make_float2(0.f, 0.f);
+        }
+        const float wa = m * m, wb = mrow ? (1.f - m) * (1.f - m) : 0.f;
+        PairAcc<D, PART, 0>::run(y, wa, wb, ps, pn);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs a) {
+    using G = ScmGeom<D>;
+    extern __shared__ float2 red[];  // [NPART][NPP][2][32]
+    const int lane = threadIdx.x & 31;
+    const int part = (threadIdx.x >> 5) % G::NPART;
+    const int tw = threadIdx.x / (32 * G::NPART);
+    const int grp = blockIdx.y;
+    const int f = blockIdx.x * 32 + lane;
+    const bool active = f < a.in.F;
+    const int fc = active ? f : a.in.F - 1;
+
+    float2 ps[G::NPP], pn[G::NPP];
+#pragma unroll
+    for (int q = 0; q < G::NPP; ++q) ps[q] = pn[q] = make_float2(0.f, 0.f);
+
+    switch (part) {  // warp-uniform: keeps the (i, j) of every accumulator compile-time
+        case 0: scm_accumulate<D, 0>(a, grp, fc, active, tw, ps, pn); break;
+        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+    }
+
+    // reduce the TW time-ways in fixed order: way w adds into way 0 through shared memory
+    float2* mine = red + (size_t)part * G::NPP * 2 * 32;
+    for (int w = 1; w < G::TW; ++w) {
+        if (tw == w) {
+#pragma unroll
+            for (int q = 0; q < G::NPP; ++q) {
+                mine[(q * 2 + 0) * 32 + lane] = ps[q];
+                mine[(q * 2 + 1) * 32 + lane] = pn[q];
+            }
+        }
+        __syncthreads();
+        if (tw == 0) {
+#pragma unroll
+            for (int q = 0; q < G::NPP; ++q) {
+                ps[q] = cadd(ps[q], mine[(q * 2 + 0) * 32 + lane]);
+                pn[q] = cadd(pn[q], mine[(q * 2 + 1) * 32 + lane]);
+            }
+        }
+        __syncthreads();
+    }
+    if (tw == 0 && active) {
+        const float inv_T = 1.0f / (float)a.in.T;
+        float2* Rs = a.Rss + ((size_t)grp * a.in.F + f) * D * D;
+        float2* Rn = a.Rnn + ((size_t)grp * a.in.F + f) * D * D;
+#pragma unroll
+        for (int q = 0; q < G::NPP; ++q) {
+            // `part` is runtime here; recover (i, j) arithmetically (tiny epilogue, not the hot loop)
+            int pidx = q * G::NPART + part;
+            if (pidx < G::NPAIR) {
+                int i = 0, n = D, pp = pidx;
+                while (pp >= n) {
+                    pp -= n;
+                    --n;
+                    ++i;
+                }
+                const int j = i + pp;
+                float2 s = cscale(ps[q], inv_T), nn = cscale(pn[q], inv_T);
+                if (i == j) s.y = 0.f, nn.y = 0.f;
+                Rs[i * D + j] = s;
+                Rn[i * D + j] = nn;
+                if (i != j) {
+                    Rs[j * D + i] = cconj(s);
+                    Rn[j * D + i] = cconj(nn);
+                }
+            }
+        }
+    }
+}
+
+template <int D>
+static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
+    using G = ScmGeom<D>;
+    const size_t smem = (size_t)G::NPART * G::NPP * 2 * 32 * sizeof(float2);
+    auto kern = masked_scm_kernel<D>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((a.in.F + 31) / 32, a.in.n_grp);
+    kern<<<grid, G::THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st) {
+    const int D = a.in.C + a.in.K - 1;
+    switch (D) {
+        case 1: return launch_d<1>(a, st);
+        case 2: return launch_d<2>(a, st);
+        case 3: return launch_d<3>(a, st);
+        case 4: return launch_d<4>(a, st);
+        case 5: return launch_d<5>(a, st);
+        case 6: return launch_d<6>(a, st);
+        case 7: return launch_d<7>(a, st);
+        case 8: return launch_d<8>(a, st);
+        case 9: return launch_d<9>(a, st);
+        case 10: return launch_d<10>(a, st);
+        case 11: return launch_d<11>(a, st);
+        case 12: return launch_d<12>(a, st);
+        case 13: return launch_d<13>(a, st);
+        case 14: return launch_d<14>(a, st);
+        case 15: return launch_d<15>(a, st);
+        case 16: return launch_d<16>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace disco

@@ -1,0 +1,271 @@
+// Per-bin multichannel-Wiener-filter solve: replaces intern_filter
+// (reference se_utils/internal_formulas.py:31-81) for a whole batch of bins in one launch.
+//
+//   'gevd'   (:56-73)  rank-r GEVD-MWF.  Closed form of Q D (D + mu I)^-1 Q^-1 [:, 0]:
+//            with (lambda_i, q_i) the generalised eigenpairs of (Rss, Rnn), q_i^H Rnn q_i = 1,
+//            lambda clamped to [eps, 1e6] and sorted descending,
+//                w  = sum_{i<r} q_i * lambda_i / (lambda_i + mu) * conj((Rnn q_i)[0])
+//                t1 = q_0 * conj((Rnn q_0)[0])
+//            computed as: Cholesky Rnn = L L^H, A = L^-1 Rss L^-H, cyclic complex Jacobi on A,
+//            q = L^-H v.  (scipy.linalg.eig / cggev in the reference; same pairs for a
+//            Hermitian-definite pencil.)
+//   'r1-mwf' (:45-54)  w = l u conj(v_0) / (mu + l v^H u), (l, v) top eigenpair of Rss, u = Rnn^-1 v
+//   'mwf'    (:74-76)  w = (Rnn + Rss)^-1 Rss e_0
+//
+// One thread per matrix, float64 throughout (the SCMs arrive as complex64): the work is
+// O(n_mat * D^3) flops -- negligible next to the streaming kernels -- and double precision
+// keeps the result far inside the 1e-5 parity budget even for ill-conditioned bins.
+// Degenerate bins: a Cholesky pivot below 1e-13 * trace/D is floored there (diagonal
+// loading) so the output stays finite where LAPACK would return inf/NaN eigenvalues.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace disco {
+
+struct cd {
+    double x, y;
+};
+DISCO_DEV cd mk(double x, double y) { return cd{x, y}; }
+DISCO_DEV cd operator+(cd a, cd b) { return cd{a.x + b.x, a.y + b.y}; }
+DISCO_DEV cd operator-(cd a, cd b) { return cd{a.x - b.x, a.y - b.y}; }
+DISCO_DEV cd operator*(cd a, cd b) { return cd{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+DISCO_DEV cd operator*(double s, cd a) { return cd{s * a.x, s * a.y}; }
+DISCO_DEV cd conj(cd a) { return cd{a.x, -a.y}; }
+DISCO_DEV double norm2(cd a) { return a.x * a.x + a.y * a.y; }
+
+constexpr double kEps = 2.220446049250313e-16;  // sys.float_info.epsilon (internal_formulas.py:6)
+constexpr double kEta = 1e6;                    // internal_formulas.py:7
+
+// In-place lower Cholesky of the Hermitian matrix M (uses the lower triangle); returns L in M's
+// lower triangle with real positive diagonal.  Pivots are floored at `floor_`.
+template <int D>
+DISCO_DEV void cholesky(cd (&M)[D][D], double floor_) {
+#pragma unroll 1
+    for (int j = 0; j < D; ++j) {
+        double d = M[j][j].x;
+        for (int k = 0; k < j; ++k) d -= norm2(M[j][k]);
+        d = fmax(d, floor_);
+        const double l = sqrt(d), inv = 1.0 / l;
+        M[j][j] = mk(l, 0.0);
+        for (int i = j + 1; i < D; ++i) {
+            cd s = M[i][j];
+            for (int k = 0; k < j; ++k) s = s - M[i][k] * conj(M[j][k]);
+            M[i][j] = inv * s;
+        }
+    }
+}
+
+// Cyclic Jacobi for a Hermitian matrix A (destroyed); V receives the eigenvectors (columns),
+// lam the eigenvalues (unsorted).
+template <int D>
+DISCO_DEV void jacobi(cd (&A)[D][D], cd (&V)[D][D], double (&lam)[D]) {
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
+    double tot = 0.0;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) tot += norm2(A[i][j]);
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < D; ++p)
+            for (int q = p + 1; q < D; ++q) off += norm2(A[p][q]);
+        if (off <= 1e-30 * tot) break;
+#pragma unroll 1
+        for (int p = 0; p < D - 1; ++p) {
+#pragma unroll 1
+            for (int q = p + 1; q < D; ++q) {
+                const cd b = A[p][q];
+                const double ab = sqrt(norm2(b));
+                if (ab < 1e-300) continue;
+                const cd ph = (1.0 / ab) * b;
+                const double tau = (A[q][q].x - A[p][p].x) / (2.0 * ab);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+                const cd st = s * ph, stc = conj(st);
+                for (int k = 0; k < D; ++k) {  // A <- A G
+                    const cd akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - stc * akq;
+                    A[k][q] = st * akp + c * akq;
+                }
+                for (int k = 0; k < D; ++k) {  // A <- G^H A
+                    const cd apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - st * aqk;
+                    A[q][k] = stc * apk + c * aqk;
+                }
+                A[p][q] = mk(0.0, 0.0);
+                A[q][p] = mk(0.0, 0.0);
+                A[p][p].y = 0.0;
+                A[q][q].y = 0.0;
+                for (int k = 0; k < D; ++k) {  // V <- V G
+                    const cd vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - stc * vkq;
+                    V[k][q] = st * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < D; ++i) lam[i] = A[i][i].x;
+}
+
+template <int D>
+DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][D]) {
+    // Hermitian-symmetrise: the SCM kernels write exact conjugate mirrors, user input may not
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j <= i; ++j) {
+            const float2 a = R[i * D + j], b = R[j * D + i];
+            const cd v = mk(0.5 * ((double)a.x + (double)b.x), 0.5 * ((double)a.y - (double)b.y));
+            M[i][j] = v;
+            M[j][i] = conj(v);
+        }
+}
+
+template <int D>
+__global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_mat) return;
+    const float2* Rs = a.Rss + (size_t)idx * D * D;
+    const float2* Rn = a.Rnn + (size_t)idx * D * D;
+    cd S[D][D], Nn[D][D], V[D][D];
+    cd w[D], t1[D];
+    for (int i = 0; i < D; ++i) t1[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);   // e_0 (internal_formulas.py:43)
+    load_herm<D>(Rs, S);
+    load_herm<D>(Rn, Nn);
+    double trn = 0.0, trs = 0.0;
+    for (int i = 0; i < D; ++i) trn += Nn[i][i].x, trs += S[i][i].x;
+
+    if (a.type == 0) {  // ------------------------------------------------------------ gevd
+        cd Lm[D][D];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
+        cholesky<D>(Lm, 1e-13 * trn / D + 1e-300);
+        // M = L^-1 S  (forward substitution, column by column), stored in S
+        for (int col = 0; col < D; ++col)
+            for (int i = 0; i < D; ++i) {
+                cd s = S[i][col];
+                for (int k = 0; k < i; ++k) s = s - Lm[i][k] * S[k][col];
+                S[i][col] = (1.0 / Lm[i][i].x) * s;
+            }
+        // A = M L^-H  <=>  A^H = L^-1 M^H ; do it row-wise: for each row r of M solve x L^H = M[r]
+        for (int r = 0; r < D; ++r)
+            for (int j = 0; j < D; ++j) {
+                cd s = S[r][j];
+                for (int k = 0; k < j; ++k) s = s - S[r][k] * conj(Lm[j][k]);
+                S[r][j] = (1.0 / Lm[j][j].x) * s;
+            }
+        for (int i = 0; i < D; ++i)   // enforce exact Hermitian symmetry
+            for (int j = 0; j < i; ++j) {
+                cd v = 0.5 * (S[i][j] + conj(S[j][i]));
+                S[i][j] = v;
+                S[j][i] = conj(v);
+            }
+        double lam[D];
+        jacobi<D>(S, V, lam);
+        // Q = L^-H V : back substitution on each eigenvector
+        for (int col = 0; col < D; ++col)
+            for (int i = D - 1; i >= 0; --i) {
+                cd s = V[i][col];
+                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * V[k][col];
+                V[i][col] = (1.0 / Lm[i][i].x) * s;
+            }
+        for (int i = 0; i < D; ++i) w[i] = mk(0.0, 0.0);
+        const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
+        bool used[D];
+        for (int i = 0; i < D; ++i) used[i] = false;
+        for (int r = 0; r < rank; ++r) {  // r-th largest eigenvalue (selection, stable for ties)
+            int best = -1;
+            for (int i = 0; i < D; ++i)
+                if (!used[i] && (best < 0 || lam[i] > lam[best])) best = i;
+            used[best] = true;
+            const double l = fmin(fmax(lam[best], kEps), kEta);
+            cd c0 = mk(0.0, 0.0);  // (Rnn q)[0]
+            for (int j = 0; j < D; ++j) c0 = c0 + Nn[0][j] * V[j][best];
+            const cd cc = conj(c0);
+            const double g = l / (l + a.mu);
+            for (int i = 0; i < D; ++i) {
+                const cd qc = V[i][best] * cc;
+                w[i] = w[i] + g * qc;
+                if (r == 0) t1[i] = qc;
+            }
+        }
+    } else if (a.type == 1) {  // -------------------------------------------------- r1-mwf
+        cd Lm[D][D];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
+        double lam[D];
+        jacobi<D>(S, V, lam);
+        int best = 0;
+        for (int i = 1; i < D; ++i)
+            if (lam[i] > lam[best]) best = i;
+        const double l = fabs(lam[best]);
+        cholesky<D>(Lm, 1e-13 * trn / D + 1e-300);
+        cd u[D];
+        for (int i = 0; i < D; ++i) {  // L y = v
+            cd s = V[i][best];
+            for (int k = 0; k < i; ++k) s = s - Lm[i][k] * u[k];
+            u[i] = (1.0 / Lm[i][i].x) * s;
+        }
+        for (int i = D - 1; i >= 0; --i) {  // L^H u = y
+            cd s = u[i];
+            for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * u[k];
+            u[i] = (1.0 / Lm[i][i].x) * s;
+        }
+        cd vhu = mk(0.0, 0.0);
+        for (int i = 0; i < D; ++i) vhu = vhu + conj(V[i][best]) * u[i];
+        // w = l u conj(v0) / (mu + l v^H u); the denominator is real for Hermitian Rnn
+        const cd den = mk(a.mu + l * vhu.x, l * vhu.y);
+        const double dn = 1.0 / norm2(den);
+        const cd inv = mk(den.x * dn, -den.y * dn);
+        const cd sc = (l * conj(V[0][best])) * inv;
+        for (int i = 0; i < D; ++i) w[i] = u[i] * sc;
+    } else {  // ------------------------------------------------------------------------ mwf
+        cd Lm[D][D];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j] + S[i][j];
+        cholesky<D>(Lm, 1e-13 * (trn + trs) / D + 1e-300);
+        for (int i = 0; i < D; ++i) {  // L y = Rss[:, 0]
+            cd s = S[i][0];
+            for (int k = 0; k < i; ++k) s = s - Lm[i][k] * w[k];
+            w[i] = (1.0 / Lm[i][i].x) * s;
+        }
+        for (int i = D - 1; i >= 0; --i) {
+            cd s = w[i];
+            for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * w[k];
+            w[i] = (1.0 / Lm[i][i].x) * s;
+        }
+    }
+    for (int i = 0; i < D; ++i) {
+        a.W[(size_t)idx * D + i] = make_float2((float)w[i].x, (float)w[i].y);
+        if (a.T1) a.T1[(size_t)idx * D + i] = make_float2((float)t1[i].x, (float)t1[i].y);
+    }
+}
+
+template <int D>
+static cudaError_t launch_d(const SolveArgs& a, cudaStream_t st) {
+    mwf_solve_kernel<D><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mwf_solve(const SolveArgs& a, cudaStream_t st) {
+    if (a.n_mat <= 0) return cudaSuccess;
+    switch (a.D) {
+        case 1: return launch_d<1>(a, st);
+        case 2: return launch_d<2>(a, st);
+        case 3: return launch_d<3>(a, st);
+        case 4: return launch_d<4>(a, st);
+        case 5: return launch_d<5>(a, st);
+        case 6: return launch_d<6>(a, st);
+        case 7: return launch_d<7>(a, st);
+        case 8: return launch_d<8>(a, st);
+        case 9: return launch_d<9>(a, st);
+        case 10: return launch_d<10>(a, st);
+        case 11: return launch_d<11>(a, st);
+        case 12: return launch_d<12>(a, st);
+        case 13: return launch_d<13>(a, st);
+        case 14: return launch_d<14>(a, st);
+        case 15: return launch_d<15>(a, st);
+        case 16: return launch_d<16>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace disco

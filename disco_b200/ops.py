@@ -1,0 +1,214 @@
+"""Tensor-level operators of the MWF path: thin wrappers that hand torch CUDA tensors (device
+memory + current stream) to the C ABI of libdisco_b200.so.  PyTorch is plumbing here: all
+arithmetic happens in the hand-written kernels.
+
+Layouts: spectra are frame-major ``[..., T, F]`` complex64; ``layout='FT'`` arguments select the
+reference's NumPy layout ``[..., F, T]`` for masks / final outputs (SURVEY.md §8b op table).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+TF, FT = 0, 1
+MASK_KINDS = {"irm": 0, "ibm": 1, "iam": 2}
+FILTER_TYPES = {"gevd": 0, "r1-mwf": 1, "mwf": 2}
+
+
+def _layout(layout):
+    if layout in (TF, "TF", "tf"):
+        return TF
+    if layout in (FT, "FT", "ft"):
+        return FT
+    raise ValueError("layout must be 'TF' or 'FT'")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (disco_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def n_frames(length, n_fft=512):
+    """1 + L // hop (reference tango.py:287)."""
+    return 1 + length // (n_fft // 2)
+
+
+def init(n_fft=512):
+    """Create the per-device FFT tables now (required before CUDA-graph capture)."""
+    _lib.check(_lib.load().disco_init(int(n_fft)))
+
+
+def stft(x, n_fft=512):
+    """x [..., L] float32 -> Y [..., T, F] complex64 (librosa center/reflect/periodic-Hann semantics)."""
+    _need(x, torch.float32, "x")
+    L = x.shape[-1]
+    n_sig = x.numel() // L
+    T, F = n_frames(L, n_fft), n_fft // 2 + 1
+    Y = torch.empty(x.shape[:-1] + (T, F), dtype=torch.complex64, device=x.device)
+    _lib.check(_lib.load().disco_stft(_ptr(x), _ptr(Y), n_sig, L, n_fft, _stream()))
+    return Y
+
+
+def stft_scm(x, mask, n_fft=512, mask_layout="TF"):
+    """Fused STFT + masked SCM.  x [G, C, L] float32, mask [G, T, F] (or [G, F, T]) float32
+    -> Y [G, C, T, F] complex64, Rss, Rnn [G, F, C, C] complex64."""
+    _need(x, torch.float32, "x")
+    _need(mask, torch.float32, "mask")
+    if x.dim() != 3:
+        raise ValueError("x must be [groups, channels, samples]")
+    G, C, L = x.shape
+    T, F = n_frames(L, n_fft), n_fft // 2 + 1
+    lay = _layout(mask_layout)
+    want = (G, T, F) if lay == TF else (G, F, T)
+    if tuple(mask.shape) != want:
+        raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
+    lib = _lib.load()
+    Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
+    Rss = torch.empty((G, F, C, C), dtype=torch.complex64, device=x.device)
+    Rnn = torch.empty_like(Rss)
+    ws_bytes = lib.disco_stft_scm_workspace(G, C, L, n_fft)
+    ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
+    _lib.check(lib.disco_stft_scm(_ptr(x), _ptr(mask), lay, _ptr(Y), _ptr(Rss), _ptr(Rnn), G, C, L, n_fft,
+                                  _ptr(ws), ws_bytes, _stream()))
+    return Y, Rss, Rnn
+
+
+def tf_mask(S, N, type="irm1", bin_thr=0.0):
+    """Oracle mask (reference dnn/utils.py:44-71) on device, float32.  Same shape as S."""
+    _need(S, torch.complex64, "S")
+    _need(N, torch.complex64, "N")
+    if S.shape != N.shape:
+        raise AssertionError("Input spectrograms should have the same shape.")   # sigproc_utils.py:71
+    kind = type[:-1] if len(type) > 1 else ""
+    if kind not in MASK_KINDS or not type[-1].isdigit():
+        raise ValueError('Unknown mask type. Should be "irmX", "ibmX" or "iamX"')
+    M = torch.empty(S.shape, dtype=torch.float32, device=S.device)
+    _lib.check(_lib.load().disco_tf_mask(_ptr(S), _ptr(N), _ptr(M), S.numel(), MASK_KINDS[kind], int(type[-1]),
+                                         float(bin_thr), _stream()))
+    return M
+
+
+def _sel(node_sel, K):
+    if node_sel is None:
+        return None, K, K
+    arr = (ctypes.c_int * len(node_sel))(*[int(v) for v in node_sel])
+    return arr, len(node_sel), len(node_sel)
+
+
+def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
+    """Y [B, Ksel, C, T, F], Z [B, K, T, F] or None (K = 1), mask [B, Ksel, T, F] / [B, Ksel, F, T] or None
+    -> Rss, Rnn [B, Ksel, F, D, D], D = C + K - 1 (own mics, then z of the other nodes)."""
+    _need(Y, torch.complex64, "Y")
+    B, Ks, C, T, F = Y.shape
+    K = 1 if Z is None else Z.shape[1]
+    if Z is not None:
+        _need(Z, torch.complex64, "Z")
+        if tuple(Z.shape) != (B, K, T, F):
+            raise ValueError("Z must be [B, K, T, F]")
+    sel, n_sel, _ = _sel(node_sel, K)
+    if Ks != n_sel:
+        raise ValueError("Y holds %d nodes, selection has %d" % (Ks, n_sel))
+    lay = _layout(mask_layout)
+    if mask is not None:
+        _need(mask, torch.float32, "mask")
+        want = (B, Ks, T, F) if lay == TF else (B, Ks, F, T)
+        if tuple(mask.shape) != want:
+            raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
+    D = C + K - 1
+    Rss = torch.empty((B, Ks, F, D, D), dtype=torch.complex64, device=Y.device)
+    Rnn = torch.empty_like(Rss)
+    _lib.check(_lib.load().disco_masked_scm(_ptr(Y), _ptr(Z), _ptr(mask), lay, _ptr(Rss), _ptr(Rnn), B, K, C, T,
+                                            n_fft, sel, n_sel, _stream()))
+    return Rss, Rnn
+
+
+def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
+    """Batched intern_filter (reference internal_formulas.py:31-81).  Rss, Rnn [..., D, D] complex64
+    -> W [..., D], t1 [..., D] complex64.  rank 'full'/'Full'/None -> all eigenpairs."""
+    _need(Rss, torch.complex64, "Rss")
+    _need(Rnn, torch.complex64, "Rnn")
+    if type not in FILTER_TYPES:
+        raise AttributeError("Unknown filter reference")       # internal_formulas.py:79
+    D = Rss.shape[-1]
+    n_mat = Rss.numel() // (D * D)
+    r = 0 if rank in ("full", "Full", None) else int(rank)
+    W = torch.empty(Rss.shape[:-1], dtype=torch.complex64, device=Rss.device)
+    T1 = torch.empty_like(W)
+    _lib.check(_lib.load().disco_mwf_solve(_ptr(Rss), _ptr(Rnn), _ptr(W), _ptr(T1), n_mat, D, FILTER_TYPES[type], r,
+                                           float(mu), _stream()))
+    return W, T1
+
+
+def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", node_sel=None):
+    """out = w^H x (conj=True) or w^T x over the concatenated channels [Y ; z of other nodes].
+    W [B, Ksel, F, D]; returns out (and resid = x[ref] - out when ref is given), [B, Ksel, T, F] or [.., F, T]."""
+    _need(W, torch.complex64, "W")
+    _need(Y, torch.complex64, "Y")
+    B, Ks, C, T, F = Y.shape
+    K = 1 if Z is None else Z.shape[1]
+    if Z is not None:
+        _need(Z, torch.complex64, "Z")
+    sel, n_sel, _ = _sel(node_sel, K)
+    D = C + K - 1
+    if tuple(W.shape) != (B, Ks, F, D):
+        raise ValueError("W shape %s, expected %s" % (tuple(W.shape), (B, Ks, F, D)))
+    lay = _layout(out_layout)
+    shape = (B, Ks, T, F) if lay == TF else (B, Ks, F, T)
+    out = torch.empty(shape, dtype=torch.complex64, device=Y.device)
+    resid = torch.empty_like(out) if ref is not None else None
+    _lib.check(_lib.load().disco_filter_sum(_ptr(W), 1 if conj else 0, _ptr(Y), _ptr(Z), _ptr(out), _ptr(resid),
+                                            0 if ref is None else int(ref), lay, B, K, C, T, n_fft, sel, n_sel,
+                                            _stream()))
+    return (out, resid) if ref is not None else out
+
+
+def istft(Y, length, n_fft=512):
+    """Y [..., T, F] complex64 -> x [..., length] float32 (librosa istft semantics, center=True)."""
+    _need(Y, torch.complex64, "Y")
+    T, F = Y.shape[-2:]
+    if F != n_fft // 2 + 1:
+        raise ValueError("last dimension must be n_fft/2 + 1 bins")
+    n_sig = Y.numel() // (T * F)
+    x = torch.empty(Y.shape[:-2] + (int(length),), dtype=torch.float32, device=Y.device)
+    _lib.check(_lib.load().disco_istft(_ptr(Y), _ptr(x), n_sig, T, int(length), n_fft, _stream()))
+    return x
+
+
+def transpose_last2(a):
+    """[..., R, C] -> [..., C, R] (contiguous) for complex64 / float32 device tensors."""
+    R, Cc = a.shape[-2:]
+    batch = a.numel() // (R * Cc) if a.numel() else 0
+    out = torch.empty(a.shape[:-2] + (Cc, R), dtype=a.dtype, device=a.device)
+    lib = _lib.load()
+    if a.dtype == torch.complex64:
+        _need(a, torch.complex64, "a")
+        _lib.check(lib.disco_transpose_c64(_ptr(a), _ptr(out), batch, R, Cc, _stream()))
+    else:
+        _need(a, torch.float32, "a")
+        _lib.check(lib.disco_transpose_f32(_ptr(a), _ptr(out), batch, R, Cc, _stream()))
+    return out
+
+
+def apply_mask(X, m, one_minus=False):
+    """m * X or (1 - m) * X elementwise (same shapes), complex64 x float32."""
+    _need(X, torch.complex64, "X")
+    _need(m, torch.float32, "m")
+    if X.shape != m.shape:
+        raise ValueError("shape mismatch")
+    out = torch.empty_like(X)
+    _lib.check(_lib.load().disco_apply_mask(_ptr(X), _ptr(m), _ptr(out), X.numel(), 1 if one_minus else 0, _stream()))
+    return out

@@ -1,0 +1,149 @@
+/* disco_b200 -- C ABI of the B200-native multichannel-Wiener-filter beamforming path.
+ *
+ * Drop-in boundary for the hot path of nfurnon/disco (reference paths relative to the
+ * reference repository root).  The reference has no FFI of its own: its boundary is a set of
+ * in-process Python functions.  Each entry point below names the reference interface it
+ * replaces; the Python-side binding (ctypes) that mirrors those signatures is
+ * disco_b200/_lib.py + disco_b200/ops.py, and INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers unless the function name ends in _host.
+ *   - complex64 = interleaved (re, im) float32 pairs ("float2").
+ *   - Spectra are FRAME-MAJOR: [signal][T frames][F = n_fft/2 + 1 bins], bins contiguous.
+ *     (The reference's NumPy arrays are (F, T) with T contiguous; layout flags select that
+ *     layout for masks and final outputs, see DISCO_LAYOUT_*.)
+ *   - hop is fixed to n_fft / 2 (reference N_FFT = 512, N_HOP = 256, tango.py:28-29);
+ *     n_fft in {256, 512, 1024}.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  No entry point
+ *     synchronises the device; work is ordered on `stream`.
+ *   - Return value: 0 on success; DISCO_ERR_* (< 0) for invalid arguments; a positive
+ *     cudaError_t value if a CUDA call failed.  disco_last_error() returns a message for the
+ *     calling thread.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DISCO_B200_H
+#define DISCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISCO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DISCO_API __attribute__((visibility("default")))
+#else
+#define DISCO_API
+#endif
+
+#define DISCO_OK 0
+#define DISCO_ERR_INVALID (-1)      /* bad size / unsupported parameter                        */
+#define DISCO_ERR_UNSUPPORTED (-2)  /* valid in the reference but not implemented here          */
+#define DISCO_ERR_WORKSPACE (-3)    /* workspace too small                                      */
+
+/* layouts of (F, T) planes */
+#define DISCO_LAYOUT_TF 0 /* frame-major: [T][F], bins contiguous (native)                      */
+#define DISCO_LAYOUT_FT 1 /* reference NumPy layout: [F][T], frames contiguous                   */
+
+/* tf_mask kinds (reference dnn/utils.py:44-71 `type` = 'irmX' | 'ibmX' | 'iamX') */
+#define DISCO_MASK_IRM 0
+#define DISCO_MASK_IBM 1
+#define DISCO_MASK_IAM 2
+
+/* intern_filter types (reference se_utils/internal_formulas.py:31-81 `type`) */
+#define DISCO_FILTER_GEVD 0
+#define DISCO_FILTER_R1_MWF 1
+#define DISCO_FILTER_MWF 2
+
+DISCO_API int disco_abi_version(void);
+DISCO_API const char* disco_last_error(void);
+
+/* Number of STFT frames for a signal of `length` samples: 1 + length / (n_fft/2)
+ * (librosa center=True; equals the reference's 3 + floor((L - N_FFT) / N_HOP), tango.py:287). */
+DISCO_API int disco_n_frames(int length, int n_fft);
+
+/* Create the per-device twiddle / window tables for n_fft ahead of time (they are otherwise
+ * created on first use, which must not happen inside CUDA-graph capture). */
+DISCO_API int disco_init(int n_fft);
+
+/* ---- STFT --------------------------------------------------------------------------------
+ * Replaces lb.core.stft(x, n_fft, hop_length=n_fft/2, center=True) [pad_mode='reflect', periodic
+ * Hann] at reference tango.py:335-337, get_z_signals.py:274-276, post_generator.py:121,
+ * math_utils.py:134-140 (my_stft), for n_sig signals at once.
+ *   x [n_sig][length] float32  ->  Y [n_sig][T][F] complex64 */
+DISCO_API int disco_stft(const float* x, void* Y, int n_sig, int length, int n_fft, void* stream);
+
+/* ---- fused STFT + mask-weighted spatial covariance ---------------------------------------------
+ * Replaces, per group (= one array node of one utterance, C microphones):
+ *   STFT of the C channels                                  tango.py:335
+ *   s_hat = m * Y, n_hat = (1 - m) * Y                      tango.py:347-348
+ *   R_ss[f] = mean_t s_hat s_hat^H, R_nn[f] likewise        tango.py:357-364 (np.outer convention
+ *                                                           R[i][j] = a_i conj(a_j))
+ *   x    [n_grp][C][length] float32
+ *   mask [n_grp] planes of (F, T) float32 in `mask_layout`
+ *   Y    [n_grp][C][T][F] complex64                (output, materialised: step 2 re-reads it)
+ *   Rss, Rnn [n_grp][F][C][C] complex64            (outputs)
+ * C <= 4 in this version (larger arrays: disco_stft + disco_masked_scm).
+ * workspace: disco_stft_scm_workspace() bytes of device scratch. */
+DISCO_API size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft);
+DISCO_API int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn,
+                   int n_grp, int C, int length, int n_fft, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ---- oracle time-frequency masks ----------------------------------------------------------------
+ * Replaces tf_mask(s, n, type, bin_thr) (reference dnn/utils.py:44-71, sigproc_utils.py:58-86).
+ * Elementwise over n_elem points; `bin_thr_db` as in the reference (dB); ibm is written 0.0/1.0. */
+DISCO_API int disco_tf_mask(const void* S, const void* N, float* M, size_t n_elem, int kind, int power,
+                  float bin_thr_db, void* stream);
+
+/* ---- mask-weighted SCM of spectra already in HBM (Tango step 2) ---------------------------------
+ * Replaces concatenate_signals + the global SCM loops (reference tango.py:142-155, 431-440) with
+ * mask_for_z = 'local': group g = (utterance b, node k) sees D = C + K - 1 channels: its own
+ * Y[g][0..C), then Z[b][j] for j != k in node order.  K = 1 (Z may be NULL) is the plain
+ * masked_scm of SURVEY.md 8(b).  mask == NULL: unweighted SCM into Rss, Rnn zero-filled.
+ * Ragged arrays (reference tango.py:259-260, 284: nodes may have different channel counts):
+ * launch once per channel count with node_sel = the ascending HOST array of the n_sel node
+ * indices that have C microphones (Y, mask, outputs then hold n_utt * n_sel groups);
+ * node_sel == NULL means all K nodes.
+ *   Y [n_utt*K][C][T][F], Z [n_utt][K][T][F] complex64; mask [n_utt*K] planes; Rss/Rnn [n_utt*K][F][D][D] */
+DISCO_API int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_layout, void* Rss, void* Rnn,
+                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, void* stream);
+
+/* ---- per-bin MWF solve ---------------------------------------------------------------------------
+ * Replaces intern_filter(Rxx, Rnn, mu, type, rank) (reference internal_formulas.py:31-81) for
+ * n_mat matrices: Rss, Rnn [n_mat][D][D] complex64 -> W [n_mat][D], T1 [n_mat][D] complex64
+ * (T1 may be NULL).  rank <= 0 means 'full'.  D <= 16.  Arithmetic in float64. */
+DISCO_API int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
+                    int rank, double mu, void* stream);
+
+/* ---- filter-and-sum ------------------------------------------------------------------------------
+ * Replaces np.inner(conj(w), x[:, f, t]) (conj_w = 1) / np.inner(t1, x[:, f, t]) (conj_w = 0) over
+ * all (f, t) (reference tango.py:369-374, 445-450) on the same concatenated channel view as
+ * disco_masked_scm, and optionally resid = x[ref] - out (zn, tango.py:376).
+ *   W [n_utt*K][F][D]; out, resid [n_utt*K] planes in `out_layout` (resid may be NULL) */
+DISCO_API int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
+                     int out_layout, int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel,
+                     void* stream);
+
+/* ---- inverse STFT --------------------------------------------------------------------------------
+ * Replaces lb.core.istft(S, hop_length=n_fft/2, win_length=n_fft, center=True, length=length)
+ * (reference tango.py:528-539, math_utils.py:143-152 my_istft).
+ *   Y [n_sig][T][F] complex64 (frame-major) -> x [n_sig][length] float32 */
+DISCO_API int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft, void* stream);
+
+/* ---- layout helpers -------------------------------------------------------------------------------
+ * out[b][c][r] = in[b][r][c] for `batch` planes (complex64 / float32).  Used at the Python
+ * boundary to move between the reference (F, T) layout and the native (T, F) layout. */
+DISCO_API int disco_transpose_c64(const void* in, void* out, int batch, int rows, int cols, void* stream);
+DISCO_API int disco_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream);
+/* out = m * in (one_minus = 0) or (1 - m) * in (one_minus = 1), elementwise (tango.py:397-398, 402-403) */
+DISCO_API int disco_apply_mask(const void* in, const float* m, void* out, size_t n_elem, int one_minus, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCO_B200_H */

@@ -1,0 +1,203 @@
+"""GPU parity tests: every kernel through the C ABI (ctypes -> libdisco_b200.so) against the CPU
+oracle on the same seeded inputs, plus the reference's own outputs (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_l2_mag
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+@pytest.mark.parametrize("n_sig,length", [(1, 4000), (2, 16000), (3, 5001), (4, 8192), (7, 6002), (9, 3000)])
+def test_stft_matches_oracle(dev, n_fft, n_sig, length):
+    from disco_b200 import ops
+    from oracle import librosa_np
+    rng = np.random.default_rng(n_sig * 1000 + length)
+    x = rng.standard_normal((n_sig, length)).astype(np.float32)
+    Y = _np(ops.stft(torch.from_numpy(x).to(dev), n_fft))
+    assert Y.shape == (n_sig, 1 + length // (n_fft // 2), n_fft // 2 + 1)
+    for i in range(n_sig):
+        ref = librosa_np.stft(x[i], n_fft, n_fft // 2).T
+        assert rel_l2(Y[i], ref) < 2e-6, (i, rel_l2(Y[i], ref))
+        assert np.max(np.abs(Y[i] - ref)) < 2e-5 * np.max(np.abs(ref))
+    assert np.all(Y[..., 0].imag == 0) and np.all(Y[..., -1].imag == 0)
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+@pytest.mark.parametrize("G,C,length", [(1, 2, 64000), (3, 4, 9000), (2, 3, 5003), (5, 1, 4000), (70, 4, 6000)])
+@pytest.mark.parametrize("layout", ["TF", "FT"])
+def test_stft_scm_matches_oracle(dev, n_fft, G, C, length, layout):
+    from disco_b200 import ops
+    from oracle import librosa_np, tango_f64
+    if layout == "FT" and G > 3:
+        pytest.skip("layout variant covered on the small cases")
+    rng = np.random.default_rng(G * 100 + C)
+    x = rng.standard_normal((G, C, length)).astype(np.float32)
+    T, F = 1 + length // (n_fft // 2), n_fft // 2 + 1
+    m = rng.uniform(size=(G, T, F)).astype(np.float32)
+    md = torch.from_numpy(m if layout == "TF" else np.ascontiguousarray(m.transpose(0, 2, 1))).to(dev)
+    Y, Rss, Rnn = ops.stft_scm(torch.from_numpy(x).to(dev), md, n_fft, mask_layout=layout)
+    Y, Rss, Rnn = _np(Y), _np(Rss), _np(Rnn)
+    for g in range(min(G, 4)):
+        Yref = np.array([librosa_np.stft(x[g, c].astype(np.float64), n_fft, n_fft // 2, dtype=np.complex128)
+                         for c in range(C)])                  # (C, F, T)
+        assert rel_l2(Y[g].transpose(0, 2, 1), Yref) < 2e-6
+        Rs, Rn = tango_f64.masked_scm(Yref, m[g].T)
+        assert rel_l2(Rss[g], Rs) < 3e-6, rel_l2(Rss[g], Rs)
+        assert rel_l2(Rnn[g], Rn) < 3e-6
+        # exact Hermitian symmetry with real diagonal
+        assert np.array_equal(Rss[g], Rss[g].conj().transpose(0, 2, 1))
+    # deterministic: a second run is bit-identical
+    Y2, Rss2, _ = ops.stft_scm(torch.from_numpy(x).to(dev), md, n_fft, mask_layout=layout)
+    assert np.array_equal(_np(Rss2), Rss) and np.array_equal(_np(Y2), Y)
+
+
+@pytest.mark.parametrize("K,C", [(1, 1), (1, 4), (1, 8), (2, 3), (4, 4), (8, 2), (3, 14), (1, 16)])
+@pytest.mark.parametrize("layout", ["TF", "FT"])
+def test_masked_scm_matches_oracle(dev, K, C, layout):
+    from disco_b200 import ops
+    from oracle import tango_f64
+    rng = np.random.default_rng(K * 17 + C)
+    B, T, F = 2, 75, 257
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, Z = cplx(B, K, C, T, F), cplx(B, K, T, F)
+    m = rng.uniform(size=(B, K, T, F)).astype(np.float32)
+    md = torch.from_numpy(m if layout == "TF" else np.ascontiguousarray(m.transpose(0, 1, 3, 2))).to(dev)
+    Rss, Rnn = ops.masked_scm(torch.from_numpy(Y).to(dev), md, torch.from_numpy(Z).to(dev) if K > 1 else None,
+                              mask_layout=layout)
+    Rss, Rnn = _np(Rss), _np(Rnn)
+    D = C + K - 1
+    assert Rss.shape == (B, K, F, D, D)
+    for b in range(B):
+        for k in range(K):
+            X = np.concatenate([Y[b, k], Z[b, [j for j in range(K) if j != k]]], axis=0)   # (D, T, F)
+            Rs, Rn = tango_f64.masked_scm(X.transpose(0, 2, 1), m[b, k].T)
+            assert rel_l2(Rss[b, k], Rs) < 2e-6
+            assert rel_l2(Rnn[b, k], Rn) < 2e-6
+    # no mask: plain SCM, Rnn = 0
+    R1, R0 = ops.masked_scm(torch.from_numpy(Y).to(dev), None, torch.from_numpy(Z).to(dev) if K > 1 else None)
+    X = np.concatenate([Y[0, 0], Z[0, 1:]], axis=0) if K > 1 else Y[0, 0]
+    assert rel_l2(_np(R1)[0, 0], tango_f64.scm(X.transpose(0, 2, 1))) < 2e-6
+    assert not np.any(_np(R0))
+
+
+def test_mwf_solve_reference_kats(dev):
+    """intern_filter known answers produced by the reference itself (oracle/make_golden.py)."""
+    from disco_b200 import ops
+    g = load_golden("intern_filter_kat")
+    for i in range(int(g["count"])):
+        typ, rank, mu = str(g["cfg_%d" % i]).split("|")
+        rank = 1 if rank == "None" else (rank if rank == "full" else int(rank))
+        Rxx = torch.from_numpy(g["Rxx_%d" % i].astype(np.complex64)).to(dev)
+        Rnn = torch.from_numpy(g["Rnn_%d" % i].astype(np.complex64)).to(dev)
+        W, t1 = ops.mwf_solve(Rxx[None], Rnn[None], float(mu), typ, rank)
+        tol = 5e-4 if g["Rxx_%d" % i].dtype == np.complex64 else 1e-5   # c64 KATs carry cggev's fp32 noise
+        assert rel_l2(_np(W)[0], g["W_%d" % i]) < tol, (i, typ, rank, rel_l2(_np(W)[0], g["W_%d" % i]))
+        assert rel_l2(_np(t1)[0], g["t1_%d" % i]) < tol, (i, typ, rank)
+    with pytest.raises(AttributeError):
+        ops.mwf_solve(Rxx[None], Rnn[None], 1.0, "nope", 1)
+
+
+@pytest.mark.parametrize("D", [1, 2, 4, 7, 9, 12, 16])
+def test_mwf_solve_matches_f64(dev, D):
+    from disco_b200 import ops
+    from oracle import tango_f64
+    rng = np.random.default_rng(D)
+    n = 300
+    def hpd(r):
+        a = rng.standard_normal((n, D, r)) + 1j * rng.standard_normal((n, D, r))
+        return a @ a.conj().transpose(0, 2, 1) / r
+    Rss = (hpd(D + 2) * 0.1 + 3 * hpd(1)).astype(np.complex64)
+    Rnn = hpd(D + 3).astype(np.complex64)
+    for typ, rank, mu in (("gevd", 1, 1.0), ("gevd", min(2, D), 2.0), ("gevd", "full", 1.0), ("mwf", 1, 1.0),
+                          ("r1-mwf", 1, 1.5)):
+        W, t1 = ops.mwf_solve(torch.from_numpy(Rss).to(dev), torch.from_numpy(Rnn).to(dev), mu, typ, rank)
+        R64s, R64n = Rss.astype(np.complex128), Rnn.astype(np.complex128)
+        if typ == "gevd":
+            wref, tref, _ = tango_f64.gevd_filter(R64s, R64n, mu, rank)
+            assert rel_l2(_np(t1), tref) < 1e-5
+        else:
+            wref = tango_f64.solve(R64s, R64n, mu, typ)
+        assert rel_l2(_np(W), wref) < 1e-5, (typ, rank, rel_l2(_np(W), wref))
+    # identities: full-rank gevd == mwf; t1 = w (lambda+mu)/lambda for rank 1
+    Wg, _ = ops.mwf_solve(torch.from_numpy(Rss).to(dev), torch.from_numpy(Rnn).to(dev), 1.0, "gevd", "full")
+    Wm, _ = ops.mwf_solve(torch.from_numpy(Rss).to(dev), torch.from_numpy(Rnn).to(dev), 1.0, "mwf", 1)
+    assert rel_l2(_np(Wg), _np(Wm)) < 1e-5
+
+
+@pytest.mark.parametrize("K,C", [(1, 2), (1, 4), (4, 4), (8, 2), (2, 15)])
+def test_filter_sum_matches_oracle(dev, K, C):
+    from disco_b200 import ops
+    rng = np.random.default_rng(K + C)
+    B, T, F = 2, 70, 257
+    D = C + K - 1
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, Z, W = cplx(B, K, C, T, F), cplx(B, K, T, F), cplx(B, K, F, D)
+    Yd, Zd, Wd = (torch.from_numpy(a).to(dev) for a in (Y, Z, W))
+    Zarg = Zd if K > 1 else None
+    out_tf, res_tf = ops.filter_sum(Wd, Yd, Zarg, conj=True, ref=0, out_layout="TF")
+    out_ft, res_ft = ops.filter_sum(Wd, Yd, Zarg, conj=True, ref=0, out_layout="FT")
+    out_nc = ops.filter_sum(Wd, Yd, Zarg, conj=False, out_layout="TF")
+    for b in range(B):
+        for k in range(K):
+            X = np.concatenate([Y[b, k], Z[b, [j for j in range(K) if j != k]]], axis=0).astype(np.complex128)
+            ref = np.einsum("fd,dtf->tf", W[b, k].conj().astype(np.complex128), X)
+            assert rel_l2(_np(out_tf)[b, k], ref) < 1e-6
+            assert rel_l2(_np(out_ft)[b, k], ref.T) < 1e-6
+            assert rel_l2(_np(res_tf)[b, k], X[0] - ref) < 1e-6
+            assert rel_l2(_np(res_ft)[b, k], (X[0] - ref).T) < 1e-6
+            assert rel_l2(_np(out_nc)[b, k], np.einsum("fd,dtf->tf", W[b, k].astype(np.complex128), X)) < 1e-6
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+@pytest.mark.parametrize("n_sig,length", [(1, 4000), (2, 16000), (3, 5001), (6, 64000)])
+def test_istft_matches_oracle_and_roundtrip(dev, n_fft, n_sig, length):
+    from disco_b200 import ops
+    from oracle import librosa_np
+    rng = np.random.default_rng(n_sig + length)
+    x = rng.standard_normal((n_sig, length)).astype(np.float32)
+    xd = torch.from_numpy(x).to(dev)
+    Y = ops.stft(xd, n_fft)
+    back = _np(ops.istft(Y, length, n_fft))
+    assert np.max(np.abs(back - x)) < 5e-6                     # STFT -> iSTFT round trip
+    # arbitrary (non-STFT-consistent) spectrum, shorter and longer output lengths
+    S = (rng.standard_normal(Y.shape) + 1j * rng.standard_normal(Y.shape)).astype(np.complex64)
+    for out_len in (length, length - 700, length + 900):
+        got = _np(ops.istft(torch.from_numpy(S).to(dev), out_len, n_fft))
+        for i in range(n_sig):
+            ref = librosa_np.istft(S[i].T, n_fft // 2, n_fft, length=out_len)
+            assert np.max(np.abs(got[i] - ref)) < 2e-5 * max(1.0, np.max(np.abs(ref))), (out_len, i)
+
+
+def test_tf_mask_kats(dev):
+    from disco_b200 import ops
+    g = load_golden("helpers_kat")
+    s, n = torch.from_numpy(g["s"]).to(dev), torch.from_numpy(g["n"]).to(dev)
+    for typ in ("irm1", "irm2", "ibm1", "ibm2", "iam1", "iam2"):
+        got = _np(ops.tf_mask(s, n, typ))
+        ref = g["dnn_" + typ].astype(np.float32)
+        ok = np.isfinite(ref)
+        assert np.max(np.abs(got[ok] - ref[ok])) < 1e-6, typ
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) or typ.startswith("iam")
+    assert np.array_equal(_np(ops.tf_mask(s, n, "ibm1", bin_thr=3)) > 0.5, g["dnn_ibm1_thr3"])
+    with pytest.raises(ValueError):
+        ops.tf_mask(s, n, "foo1")
+
+
+def test_requires_cuda_tensors(dev):
+    from disco_b200 import ops
+    with pytest.raises(TypeError):
+        ops.stft(torch.zeros(1, 4000))           # CPU tensor: no fallback

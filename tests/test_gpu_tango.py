@@ -1,0 +1,99 @@
+"""End-to-end parity of the two-step Tango MWF against the reference's own outputs (tests/golden,
+produced by the unmodified reference through oracle/ref_shim.py) and the float64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2_mag
+from oracle.make_golden import NAMES, TANGO_CASES, case_inputs, digest
+
+pytestmark = pytest.mark.gpu
+
+# north-star tolerance: <= 1e-5 relative on the beamformed STFT magnitudes, per (utterance, node)
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+GPU_CASES = [c for c in sorted(TANGO_CASES) if "ivad" not in c]
+
+
+@pytest.mark.parametrize("name", GPU_CASES)
+def test_offline_tango_matches_reference(dev, name):
+    from disco_b200.tango import offline_tango
+    seed, chans, length, vads, mfz, keep = TANGO_CASES[name]
+    g = load_golden(name)
+    y, s, n = case_inputs(seed, chans, length, vads)
+    assert digest(y) == str(g["input_sha256"])
+    res = offline_tango(y, s, n, list(vads), [None, None], mfz)
+    assert len(res) == 9
+    for nm, val in zip(NAMES, res):
+        assert len(val) == len(chans)
+        for k in range(len(chans)):
+            key = "%s_%d" % (nm, k)
+            if key not in g:
+                continue
+            ref, got = g[key], np.asarray(val[k])
+            assert got.shape == ref.shape, key
+            if nm.startswith("mask"):
+                if ref.dtype == bool:
+                    assert got.dtype == bool and np.mean(got != ref) < 1e-3, key
+                else:
+                    assert np.max(np.abs(got - ref)) < 1e-6, key
+            else:
+                assert got.dtype == np.complex64
+                assert rel_l2_mag(got, ref) < TOL, (key, rel_l2_mag(got, ref))
+
+
+def test_tango_batched_matches_f64_and_is_batch_invariant(dev):
+    """B=3 utterances x K=4 nodes x C=4 mics: each (utterance, node) within TOL of the float64 oracle,
+    and identical to processing the utterance alone (no cross-talk between batch entries)."""
+    from disco_b200.synth import make_batch
+    from disco_b200.tango import tango_batched
+    from oracle import tango_f64
+    B, K, C, L = 3, 4, 4, 12000
+    y, s, n = make_batch(B, K, C, L, seed0=50)
+    yd, sd, nd = (torch.from_numpy(a).to(dev) for a in (y, s, n))
+    out = tango_batched(yd, sd, nd)
+    solo = tango_batched(yd[1:2], sd[1:2], nd[1:2])
+    assert torch.equal(out["yf"][1], solo["yf"][0])
+    for b in range(B):
+        ref = tango_f64.offline_tango(y[b], s[b], n[b])
+        for k in range(K):
+            for nm in ("yf", "z_y", "sf", "nf", "z_s", "z_n"):
+                got = out[nm][b, k].cpu().numpy()
+                assert rel_l2_mag(got, ref[nm][k]) < TOL, (nm, b, k, rel_l2_mag(got, ref[nm][k]))
+
+
+def test_tango_external_masks_deployment_mode(dev):
+    """DNN-style deployment: only y and device-resident masks (frame-major), no clean components."""
+    from disco_b200.synth import make_batch
+    from disco_b200.tango import tango_batched
+    from oracle import tango_f64
+    B, K, C, L = 2, 2, 4, 16000
+    y, _, _ = make_batch(B, K, C, L, seed0=70)
+    T, F = 1 + L // 256, 257
+    rng = np.random.default_rng(3)
+    mz = rng.uniform(0.05, 0.95, size=(B, K, T, F)).astype(np.float32)
+    mw = rng.uniform(0.05, 0.95, size=(B, K, T, F)).astype(np.float32)
+    out = tango_batched(torch.from_numpy(y).to(dev), masks=(torch.from_numpy(mz).to(dev), torch.from_numpy(mw).to(dev)))
+    assert set(out) == {"yf", "z_y", "zn", "masks_z", "mask_w"}
+    for b in range(B):
+        ref = tango_f64.offline_tango(y[b], masks=(mz[b].transpose(0, 2, 1), mw[b].transpose(0, 2, 1)))
+        for k in range(K):
+            assert rel_l2_mag(out["yf"][b, k].cpu().numpy(), ref["yf"][k]) < TOL
+            assert rel_l2_mag(out["zn"][b, k].cpu().numpy(), ref["zn"][k]) < TOL
+
+
+def test_reference_error_behaviour(dev):
+    from disco_b200.tango import offline_tango
+    y, s, n = case_inputs(0, [2, 2], 4000)
+    with pytest.raises(TypeError):
+        offline_tango(y, s, n, ["irm1", "irm1"], [None, None], None)     # reference tango.py:343
+    with pytest.raises(ValueError):
+        offline_tango(y, s, n, ["foo1", "irm1"], [None, None], "local")   # reference tango.py:223
