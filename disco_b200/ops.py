@@ -119,9 +119,13 @@ def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
         _need(Z, torch.complex64, "Z")
         if tuple(Z.shape) != (B, K, T, F):
             raise ValueError("Z must be [B, K, T, F]")
-    sel, n_sel, _ = _sel(node_sel, K)
-    if Ks != n_sel:
-        raise ValueError("Y holds %d nodes, selection has %d" % (Ks, n_sel))
+    n_utt = B
+    if Z is None:            # no exchange: every (b, k) is an independent single-node problem
+        n_utt, sel, n_sel = B * Ks, None, 1
+    else:
+        sel, n_sel, _ = _sel(node_sel, K)
+        if Ks != n_sel:
+            raise ValueError("Y holds %d nodes, selection has %d" % (Ks, n_sel))
     lay = _layout(mask_layout)
     if mask is not None:
         _need(mask, torch.float32, "mask")
@@ -131,7 +135,7 @@ def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
     D = C + K - 1
     Rss = torch.empty((B, Ks, F, D, D), dtype=torch.complex64, device=Y.device)
     Rnn = torch.empty_like(Rss)
-    _lib.check(_lib.load().disco_masked_scm(_ptr(Y), _ptr(Z), _ptr(mask), lay, _ptr(Rss), _ptr(Rnn), B, K, C, T,
+    _lib.check(_lib.load().disco_masked_scm(_ptr(Y), _ptr(Z), _ptr(mask), lay, _ptr(Rss), _ptr(Rnn), n_utt, K, C, T,
                                             n_fft, sel, n_sel, _stream()))
     return Rss, Rnn
 
@@ -162,7 +166,13 @@ def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", no
     K = 1 if Z is None else Z.shape[1]
     if Z is not None:
         _need(Z, torch.complex64, "Z")
-    sel, n_sel, _ = _sel(node_sel, K)
+    n_utt = B
+    if Z is None:
+        n_utt, sel, n_sel = B * Ks, None, 1
+    else:
+        sel, n_sel, _ = _sel(node_sel, K)
+        if Ks != n_sel:
+            raise ValueError("Y holds %d nodes, selection has %d" % (Ks, n_sel))
     D = C + K - 1
     if tuple(W.shape) != (B, Ks, F, D):
         raise ValueError("W shape %s, expected %s" % (tuple(W.shape), (B, Ks, F, D)))
@@ -171,7 +181,7 @@ def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", no
     out = torch.empty(shape, dtype=torch.complex64, device=Y.device)
     resid = torch.empty_like(out) if ref is not None else None
     _lib.check(_lib.load().disco_filter_sum(_ptr(W), 1 if conj else 0, _ptr(Y), _ptr(Z), _ptr(out), _ptr(resid),
-                                            0 if ref is None else int(ref), lay, B, K, C, T, n_fft, sel, n_sel,
+                                            0 if ref is None else int(ref), lay, n_utt, K, C, T, n_fft, sel, n_sel,
                                             _stream()))
     return (out, resid) if ref is not None else out
 

@@ -28,7 +28,7 @@ TANGO_CASES = {
     "tango_k2c3_local": (1, [3, 3], 8192, ("irm1", "irm1"), "local", None),
     "tango_k3_ragged_local": (2, [2, 3, 2], 6000, ("irm1", "irm1"), "local", ("yf", "z_y", "zn", "sf")),
     "tango_k3c2_distant": (3, [2, 2, 2], 6000, ("irm1", "irm1"), "distant", ("yf", "z_y", "nf")),
-    "tango_k2c4_irm2_iam1": (4, [4, 4], 5000, ("irm2", "iam1"), "local", ("yf", "z_y", "masks_z", "mask_w")),
+    "tango_k2c4_irm2_iam1": (4, [4, 4], 24000, ("irm2", "iam1"), "local", ("yf", "z_y", "masks_z", "mask_w")),
     "tango_k2c2_ibm1": (5, [2, 2], 5000, ("ibm1", "ibm1"), "local", ("yf", "z_y", "masks_z")),
     "tango_k2c2_ivad": (6, [2, 2], 8192, ("ivad", "ivad"), "local", ("yf", "z_y", "masks_z")),
     # mask_for_z=None raises TypeError in the reference (tango.py:343 `in None`): no fixture.
