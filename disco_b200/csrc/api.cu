@@ -91,14 +91,17 @@ int sm_count() {
     return n;
 }
 
-// Split T frames of every group into chunks (multiples of the tile) so the grid fills the GPU.
-void choose_chunks(int n_grp, int T, int tile, int* n_chunk, int* fpc) {
-    const int want = sm_count() * 2;
-    int chunks = 1;
-    while (n_grp * chunks < want && (T + chunks - 1) / chunks > 4 * tile) chunks *= 2;
-    int f = ((T + chunks - 1) / chunks + tile - 1) / tile * tile;
-    *fpc = f;
-    *n_chunk = (T + f - 1) / f;
+// Persistent launch geometry of the fused STFT kernel: one CTA per SM (fewer when there are fewer tiles).
+struct StftPlan {
+    int n_cta, tiles_per_grp, slots_per_grp;
+};
+StftPlan plan_stft(int n_grp, int C, int T, int n_fft) {
+    StftPlan pl;
+    pl.tiles_per_grp = stft_tiles_per_grp(n_fft, C, T);
+    const long long total = (long long)n_grp * pl.tiles_per_grp;
+    pl.n_cta = (int)(total < sm_count() ? total : sm_count());
+    pl.slots_per_grp = stft_slots_per_grp(n_grp, pl.tiles_per_grp, pl.n_cta);
+    return pl;
 }
 
 int stft_common(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_sig,
@@ -122,20 +125,23 @@ int stft_common(const float* x, const float* mask, int mask_layout, void* Y, voi
     a.twiddle = tb.twiddle;
     a.window = tb.win_half;
     a.n_sig = n_sig;
+    a.n_grp = n_grp;
     a.L = length;
     a.T = T;
     a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
     a.use_tma = (length % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    choose_chunks(n_grp, T, stft_tile_frames(C), &a.n_chunk, &a.frames_per_chunk);
+    const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
+    a.slots_per_grp = pl.slots_per_grp;
     cudaStream_t st = (cudaStream_t)stream;
     if (scm) {
         if (!mask || !Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
         const size_t need = disco_stft_scm_workspace(n_grp, C, length, n_fft);
         if (!workspace || workspace_bytes < need) return fail(DISCO_ERR_WORKSPACE, "workspace too small");
     }
-    CU(launch_stft_scm(a, n_fft, C, n_grp, scm, st), "stft_scm launch");
+    CU(launch_stft_scm(a, n_fft, C, pl.n_cta, scm, st), "stft_scm launch");
     if (scm)
-        CU(launch_scm_finalize(a.part, (float2*)Rss, (float2*)Rnn, n_grp, a.n_chunk, C, n_fft / 2 + 1, T, st),
+        CU(launch_scm_finalize(a.part, (float2*)Rss, (float2*)Rnn, n_grp, pl.slots_per_grp, pl.tiles_per_grp,
+                               pl.n_cta, C, n_fft / 2 + 1, T, st),
            "scm_finalize launch");
     return 0;
 }
@@ -165,9 +171,8 @@ int disco_stft(const float* x, void* Y, int n_sig, int length, int n_fft, void* 
 size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft) {
     if (!valid_nfft(n_fft) || C < 1 || n_grp < 1) return 0;
     const int T = disco_n_frames(length, n_fft);
-    int n_chunk, fpc;
-    choose_chunks(n_grp, T, stft_tile_frames(C > 4 ? 4 : C), &n_chunk, &fpc);
-    return (size_t)n_grp * n_chunk * 2 * C * C * (n_fft / 2 + 1) * sizeof(float);
+    const StftPlan pl = plan_stft(n_grp, C > 4 ? 4 : C, T, n_fft);
+    return (size_t)n_grp * pl.slots_per_grp * 2 * C * C * (n_fft / 2 + 1) * sizeof(float);
 }
 
 int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_grp,

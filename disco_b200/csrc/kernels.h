@@ -9,19 +9,20 @@ struct StftArgs {
     const float* x;         // [n_sig][L] float32 time signals (n_sig = n_grp * C, last group may be short)
     const float* mask;      // SCM only: [n_grp][T][F] (mask_ft = 0) or [n_grp][F][T] (mask_ft = 1)
     float2* Y;              // [n_sig][T][F] complex64, frame-major
-    float* part;            // SCM only: [n_grp][n_chunk][2 C^2][F] partial sums
+    float* part;            // SCM only: [n_grp][slots_per_grp][2 C^2][F] partial sums per (group, CTA) segment
     const float2* twiddle;  // [N/32][32]: W_N^(l*k1)
     const float* window;    // [N]: 0.5 * periodic Hann
-    int n_sig, L, T;
-    int n_chunk, frames_per_chunk;
+    int n_sig, n_grp, L, T;
+    int slots_per_grp;
     int mask_ft;
     int use_tma;
 };
 
-cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_grp, bool scm, cudaStream_t st);
-cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int n_chunk, int C,
-                                int F, int T, cudaStream_t st);
-int stft_tile_frames(int C);
+cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool scm, cudaStream_t st);
+cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int slots_per_grp,
+                                int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st);
+int stft_tiles_per_grp(int n_fft, int C, int T);
+int stft_slots_per_grp(int n_grp, int tiles_per_grp, int n_cta);
 
 // Step-2 style input: group g = (utterance b, node k) sees D = C + K - 1 channels:
 // its own C microphone spectra, then the compressed signals z of the other nodes in node
