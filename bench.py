@@ -62,6 +62,13 @@ def _cpu_one(args):
     return time.perf_counter() - t0
 
 
+def _cpu_warm(_):
+    import scipy.linalg  # noqa: F401
+    from oracle import tango_np  # noqa: F401
+    time.sleep(0.2)
+    return 0
+
+
 def cpu_baseline(K, C, L, n_fft, budget_s=20.0, granularity="frame", procs=None):
     """frames/s of the oracle port with one utterance per host process (how the reference
     parallelises: exp/ex1/loop_tango.sh launches one process per utterance)."""
@@ -74,18 +81,40 @@ def cpu_baseline(K, C, L, n_fft, budget_s=20.0, granularity="frame", procs=None)
     Ls = min(L, (max_frames - 1) * (n_fft // 2))
     Ts = 1 + Ls // (n_fft // 2)
     ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
+    os.environ["OMP_NUM_THREADS"] = "1"          # inherited by the workers: one thread per process
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_one, [(1000 + i, K, C, Ls, n_fft, granularity) for i in range(cores)])
-    wall = time.perf_counter() - t0
+        pool.map(_cpu_warm, range(cores), chunksize=1)          # interpreter + NumPy/SciPy imports: untimed
+        t0 = time.perf_counter()
+        pool.map(_cpu_one, [(1000 + i, K, C, Ls, n_fft, granularity) for i in range(cores)], chunksize=1)
+        wall = time.perf_counter() - t0
     return {"value": cores * K * Ts / wall, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": "%d utterances (one per process) x %d node(s) x %d mics x %.2f s (%d frames), oracle/tango_np.py "
-                      "granularity=%s, includes process start-up" % (cores, K, C, Ls / 16000.0, Ts, granularity),
+                      "granularity=%s, workers pre-started" % (cores, K, C, Ls / 16000.0, Ts, granularity),
             "seconds": wall, "frames": cores * K * Ts}
 
 
 # ----------------------------------------------------------------------------------------------
 def clock_sampler(stop, out, gpu_index):
+    """Sample SM clock and throttle reasons through NVML every ~2 ms while the timed region runs."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            out.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active" for k in
+                                             ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            stop.wait(0.002)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
@@ -114,8 +143,8 @@ def summarize_clocks(samples):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")

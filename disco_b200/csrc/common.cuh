@@ -35,18 +35,22 @@ DISCO_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 DISCO_DEV void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait for the phase with the given parity.  try_wait suspends the warp in hardware for up to the
+// hinted time instead of spinning, so waiting warps do not steal issue slots from working ones.
 DISCO_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
 }
 // 1-D bulk tensor-memory-accelerator copy global -> shared, completion on an mbarrier.
 // dst, src 16-byte aligned, bytes a multiple of 16.

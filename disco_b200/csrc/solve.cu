@@ -17,6 +17,8 @@
 // keeps the result far inside the 1e-5 parity budget even for ill-conditioned bins.
 // Degenerate bins: a Cholesky pivot below 1e-13 * trace/D is floored there (diagonal
 // loading) so the output stays finite where LAPACK would return inf/NaN eigenvalues.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,10 +38,17 @@ DISCO_DEV double norm2(cd a) { return a.x * a.x + a.y * a.y; }
 constexpr double kEps = 2.220446049250313e-16;  // sys.float_info.epsilon (internal_formulas.py:6)
 constexpr double kEta = 1e6;                    // internal_formulas.py:7
 
+// Row pitch of the per-thread matrices.  D = 16 is padded to 17: with a power-of-two pitch nvcc 12.9
+// miscompiles the 'gevd' branch (the same source built for the host is correct).
+template <int D>
+struct Ld {
+    static constexpr int v = (D == 16) ? 17 : D;
+};
+
 // In-place lower Cholesky of the Hermitian matrix M (uses the lower triangle); returns L in M's
 // lower triangle with real positive diagonal.  Pivots are floored at `floor_`.
 template <int D>
-DISCO_DEV void cholesky(cd (&M)[D][D], double floor_) {
+DISCO_DEV void cholesky(cd (&M)[D][Ld<D>::v], double floor_) {
 #pragma unroll 1
     for (int j = 0; j < D; ++j) {
         double d = M[j][j].x;
@@ -58,7 +67,7 @@ DISCO_DEV void cholesky(cd (&M)[D][D], double floor_) {
 // Cyclic Jacobi for a Hermitian matrix A (destroyed); V receives the eigenvectors (columns),
 // lam the eigenvalues (unsorted).
 template <int D>
-DISCO_DEV void jacobi(cd (&A)[D][D], cd (&V)[D][D], double (&lam)[D]) {
+DISCO_DEV void jacobi(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], double (&lam)[D]) {
     for (int i = 0; i < D; ++i)
         for (int j = 0; j < D; ++j) V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
     double tot = 0.0;
@@ -108,7 +117,7 @@ DISCO_DEV void jacobi(cd (&A)[D][D], cd (&V)[D][D], double (&lam)[D]) {
 }
 
 template <int D>
-DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][D]) {
+DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][Ld<D>::v]) {
     // Hermitian-symmetrise: the SCM kernels write exact conjugate mirrors, user input may not
     for (int i = 0; i < D; ++i)
         for (int j = 0; j <= i; ++j) {
@@ -119,13 +128,14 @@ DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][D]) {
         }
 }
 
-template <int D>
-__global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_mat) return;
     const float2* Rs = a.Rss + (size_t)idx * D * D;
     const float2* Rn = a.Rnn + (size_t)idx * D * D;
-    cd S[D][D], Nn[D][D], V[D][D];
+    constexpr int LD = Ld<D>::v;
+    cd S[D][LD], Nn[D][LD], V[D][LD];
     cd w[D], t1[D];
     for (int i = 0; i < D; ++i) t1[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);   // e_0 (internal_formulas.py:43)
     load_herm<D>(Rs, S);
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
     for (int i = 0; i < D; ++i) trn += Nn[i][i].x, trs += S[i][i].x;
 
     if (a.type == 0) {  // ------------------------------------------------------------ gevd
-        cd Lm[D][D];
+        cd Lm[D][LD];
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
         cholesky<D>(Lm, 1e-13 * trn / D + 1e-300);
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
             }
         }
     } else if (a.type == 1) {  // -------------------------------------------------- r1-mwf
-        cd Lm[D][D];
+        cd Lm[D][LD];
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
         double lam[D];
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
         const cd sc = (l * conj(V[0][best])) * inv;
         for (int i = 0; i < D; ++i) w[i] = u[i] * sc;
     } else {  // ------------------------------------------------------------------------ mwf
-        cd Lm[D][D];
+        cd Lm[D][LD];
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j] + S[i][j];
         cholesky<D>(Lm, 1e-13 * (trn + trs) / D + 1e-300);
@@ -241,7 +251,11 @@ __global__ void __launch_bounds__(64) mwf_solve_kernel(SolveArgs a) {
 
 template <int D>
 static cudaError_t launch_d(const SolveArgs& a, cudaStream_t st) {
-    mwf_solve_kernel<D><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    static const bool alt = getenv("DISCO_SOLVE_ALT") != nullptr;   // debug: second register budget
+    if (alt && D == 16)
+        mwf_solve_kernel<D, (D == 16 ? 8 : 1)><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    else
+        mwf_solve_kernel<D, 1><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
     return cudaGetLastError();
 }
 

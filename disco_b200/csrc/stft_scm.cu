@@ -275,22 +275,35 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                     named_bar_sync(1, 32 * G::FFT_WARPS);
                 }
             }
+            if (nfr == TT && c_valid == C && (C % 2 == 0)) {     // full tile, all channels: no predication
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int item = w * NB + q;
-                const int tl = item / P, pr = item % P;
-                const int ca = 2 * pr, cb = 2 * pr + 1;
-                const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
-                const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
-                if (tl < nfr && cb < c_valid) {
+                for (int q = 0; q < NB; ++q) {
+                    const int item = w * NB + q;
+                    const int tl = item / P, pr = item % P;
+                    const float* xa = sm + (2 * pr) * (TT + 1) * H + tl * H + lane;
+                    const float* xb = xa + (TT + 1) * H;
 #pragma unroll
                     for (int j = 0; j < RA; ++j) v[q][j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
-                } else if (tl < nfr && ca < c_valid) {
+                }
+            } else {
 #pragma unroll
-                    for (int j = 0; j < RA; ++j) v[q][j] = make_float2(xa[32 * j] * win[j], 0.f);
-                } else {
+                for (int q = 0; q < NB; ++q) {
+                    const int item = w * NB + q;
+                    const int tl = item / P, pr = item % P;
+                    const int ca = 2 * pr, cb = 2 * pr + 1;
+                    const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
+                    const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
+                    if (tl < nfr && cb < c_valid) {
 #pragma unroll
-                    for (int j = 0; j < RA; ++j) v[q][j] = make_float2(0.f, 0.f);
+                        for (int j = 0; j < RA; ++j)
+                            v[q][j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
+                    } else if (tl < nfr && ca < c_valid) {
+#pragma unroll
+                        for (int j = 0; j < RA; ++j) v[q][j] = make_float2(xa[32 * j] * win[j], 0.f);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < RA; ++j) v[q][j] = make_float2(0.f, 0.f);
+                    }
                 }
             }
             __syncwarp();
@@ -349,16 +362,29 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
             if (SCM && it + 1 < n_it) load_mask(it + 1);          // in flight while this tile is processed
             mbar_wait(&spec_full[s], (it >> 1) & 1);
             const float2* stage = spec + s * G::SPEC;
-            float2* yout = p.Y + (((size_t)grp * C) * T + t0) * F + f;
+            float2* yc[C];   // per-channel output rows: frame offsets below are compile-time immediates
 #pragma unroll
-            for (int tl = 0; tl < TT; ++tl) {
-                if (tl < nfr) {
+            for (int c = 0; c < C; ++c) yc[c] = p.Y + (((size_t)grp * C + c) * T + t0) * F + f;
+            if (nfr == TT && c_valid == C) {                     // full tile: straight-line code
+#pragma unroll
+                for (int tl = 0; tl < TT; ++tl) {
                     float2 y[C];
                     unmix(stage, tl, f, y);
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        if (c < c_valid) yout[((size_t)c * T + tl) * F] = y[c];
+                    for (int c = 0; c < C; ++c) yc[c][tl * F] = y[c];
                     if (SCM) acc_step(y, mcur[tl]);
+                }
+            } else {
+#pragma unroll
+                for (int tl = 0; tl < TT; ++tl) {
+                    if (tl < nfr) {
+                        float2 y[C];
+                        unmix(stage, tl, f, y);
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            if (c < c_valid) yc[c][tl * F] = y[c];
+                        if (SCM) acc_step(y, mcur[tl]);
+                    }
                 }
             }
             __syncwarp();
@@ -374,36 +400,52 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
 
 // Reduce the (group, CTA) segment partials in fixed order, scale by 1/T, expand to full Hermitian
 // matrices Rss, Rnn [n_grp][F][C][C] complex64 (R[i][j] = mean_t a_i conj(a_j), np.outer convention).
+// One thread per (group, matrix, Hermitian pair, bin): bins are the fastest index so the partial
+// reads are coalesced; the work is tiny, the point is to expose enough loads to hide their latency.
 __global__ void scm_finalize_kernel(const float* __restrict__ part, float2* __restrict__ Rss,
                                     float2* __restrict__ Rnn, int n_grp, int slots_per_grp, int tiles_per_grp,
                                     int n_cta, int C, int F, float inv_T) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_grp * F) return;
-    const int g = idx / F, f = idx % F;
+    const int npair = C * (C + 1) / 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_total = (long long)n_grp * 2 * npair * F;
+    if (idx >= n_total) return;
+    const int f = (int)(idx % F);
+    long long r = idx / F;
+    const int pr = (int)(r % npair);
+    r /= npair;
+    const int which = (int)(r % 2), g = (int)(r / 2);
+    // pair index -> (i, j): diagonals first (pr < C), then the strict upper triangle row-major
+    int i, j;
+    if (pr < C) {
+        i = j = pr;
+    } else {
+        int o = pr - C;
+        i = 0;
+        int n = C - 1;
+        while (o >= n) {
+            o -= n;
+            --n;
+            ++i;
+        }
+        j = i + 1 + o;
+    }
     const long long total = (long long)n_grp * tiles_per_grp;
     const int b_first = cta_of_tile((long long)g * tiles_per_grp, total, n_cta);
     const int b_last = cta_of_tile((long long)(g + 1) * tiles_per_grp - 1, total, n_cta);
     const int n_slot = b_last - b_first + 1;
-    const int nacc = 2 * C * C;
-    for (int which = 0; which < 2; ++which) {
-        float2* R = (which == 0 ? Rss : Rnn) + ((size_t)g * F + f) * C * C;
-        const int base = which * C * C;
-        auto sum = [&](int a) {
-            float s = 0.f;
-            for (int sl = 0; sl < n_slot; ++sl)
-                s += part[(((size_t)g * slots_per_grp + sl) * nacc + base + a) * F + f];
-            return s * inv_T;
-        };
-        for (int i = 0; i < C; ++i) R[i * C + i] = make_float2(sum(i), 0.f);
-        int o = 0;
-        for (int i = 0; i < C; ++i)
-            for (int j = i + 1; j < C; ++j) {
-                const float re = sum(C + 2 * o), im = sum(C + 2 * o + 1);
-                R[i * C + j] = make_float2(re, im);
-                R[j * C + i] = make_float2(re, -im);
-                ++o;
-            }
+    const int nacc = 2 * C * C, base = which * C * C;
+    const int a_re = (i == j) ? i : C + 2 * (pr - C);
+    float re = 0.f, im = 0.f;
+    for (int sl = 0; sl < n_slot; ++sl) {
+        const float* q = part + (((size_t)g * slots_per_grp + sl) * nacc + base) * F + f;
+        re += q[(size_t)a_re * F];
+        if (i != j) im += q[(size_t)(a_re + 1) * F];
     }
+    re *= inv_T;
+    im *= inv_T;
+    float2* R = (which == 0 ? Rss : Rnn) + ((size_t)g * F + f) * C * C;
+    R[i * C + j] = make_float2(re, im);
+    if (i != j) R[j * C + i] = make_float2(re, -im);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -462,9 +504,9 @@ cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool
 
 cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int slots_per_grp,
                                 int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st) {
-    const int total = n_grp * F;
-    scm_finalize_kernel<<<(total + 127) / 128, 128, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp,
-                                                             n_cta, C, F, 1.0f / (float)T);
+    const long long total = (long long)n_grp * C * (C + 1) * F;   // 2 matrices x C(C+1)/2 pairs x F bins
+    scm_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp,
+                                                                        tiles_per_grp, n_cta, C, F, 1.0f / (float)T);
     return cudaGetLastError();
 }
 
