@@ -69,11 +69,28 @@ def _cpu_warm(_):
     return 0
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask and cgroup CPU quota, capped at 64
+    workers so the bounded sample stays bounded."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(K, C, L, n_fft, budget_s=20.0, granularity="frame", procs=None):
     """frames/s of the oracle port with one utterance per host process (how the reference
     parallelises: exp/ex1/loop_tango.sh launches one process per utterance)."""
     import multiprocessing as mp
-    cores = procs or os.cpu_count() or 1
+    cores = procs or usable_cores()
     T = 1 + L // (n_fft // 2)
     # bound the sample: shorten the utterance so one of them takes <~ budget (the reference runs ~120 frames/s/core)
     est_rate = 110.0 if granularity == "frame" else 20000.0
@@ -289,7 +306,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg = stft_scm_bytes(C, L, n_fft) * B * K
         achieved = alg / (kern_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "stft_scm_kernel<%d,%d,true> (+scm_finalize)" % (n_fft, C), "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "stft_scm_kernel<%d,%d,true>" % (n_fft, C), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / args.steps)}
         res = {"metric": "beamformed frames/sec (16kHz, 512-pt STFT)", "value": value, "unit": "frames/s", "n_gpus": world,

@@ -237,6 +237,26 @@ int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_l
     return 0;
 }
 
+int disco_filter_sum_scm(const void* W1, const void* Y, const float* mask, int mask_layout, void* z_out, void* zn_out,
+                         int ref, void* Rss, void* Rnn, int n_grp, int C, int T, int n_fft, void* stream) {
+    ScmArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_cat(&a.in, Y, nullptr, n_grp, 1, C, T, n_fft, nullptr, 0);
+    if (rc) return rc;
+    if (!W1 || !z_out || !Rss || !Rnn || !mask) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (ref < 0 || ref >= C) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    a.mask = mask;
+    a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
+    a.Rss = (float2*)Rss;
+    a.Rnn = (float2*)Rnn;
+    a.W1 = (const float2*)W1;
+    a.z_out = (float2*)z_out;
+    a.zn_out = (float2*)zn_out;
+    a.ref = ref;
+    CU(launch_masked_scm(a, (cudaStream_t)stream), "filter_sum_scm launch");
+    return 0;
+}
+
 int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
                     int rank, double mu, void* stream) {
     if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");

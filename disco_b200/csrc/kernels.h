@@ -44,6 +44,11 @@ struct ScmArgs {
     int mask_ft;
     float2* Rss;         // [n_grp][F][D][D]
     float2* Rnn;
+    // optional fused step-1 filter-and-sum (single-node groups, K == 1): z = w1^H y, zn = y[ref] - z
+    const float2* W1;    // [n_grp][F][C] or null
+    float2* z_out;       // [n_grp][T][F]
+    float2* zn_out;      // [n_grp][T][F] or null
+    int ref;
 };
 cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st);
 

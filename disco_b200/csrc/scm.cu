@@ -77,7 +77,7 @@ struct PairAcc {
     }
 };
 
-template <int D, int PART>
+template <int D, int PART, bool ZF>
 DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int tw,
                               float2 (&ps)[ScmGeom<D>::NPP], float2 (&pn)[ScmGeom<D>::NPP]) {
     using G = ScmGeom<D>;
@@ -88,7 +88,55 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
     const float* mrow = a.mask ? (a.mask_ft ? a.mask + ((size_t)grp * F + f) * T : a.mask + (size_t)grp * T * F + f)
                                : nullptr;
     const size_t mstride = a.mask_ft ? 1 : F;
-    for (int t = tw; t < T; t += G::TW) {
+    // fused step-1 filter (only the first pair-partition writes; K == 1 so D == C)
+    constexpr bool zfuse = ZF && (PART == 0);
+    float2 w1[D];
+    if (zfuse) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) w1[d] = cconj(a.W1[((size_t)grp * F + f) * D + d]);
+    }
+    float2* zrow = zfuse ? a.z_out + (size_t)grp * T * F + f : nullptr;
+    float2* znrow = (zfuse && a.zn_out) ? a.zn_out + (size_t)grp * T * F + f : nullptr;
+    auto point = [&](const float2 (&y)[D], float m, int t) {
+        const float wa = m * m, wb = mrow ? (1.f - m) * (1.f - m) : 0.f;
+        PairAcc<D, PART, 0>::run(y, wa, wb, ps, pn);
+        if (zfuse && active) {
+            float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < D; ++d) z = cadd(z, cmul(w1[d], y[d]));
+            zrow[(size_t)t * F] = z;
+            if (znrow) {
+                float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d == a.ref) r = y[d];
+                znrow[(size_t)t * F] = csub(r, z);
+            }
+        }
+    };
+    int t = tw;
+    // two frames per iteration: twice the loads in flight per thread
+    for (; t + G::TW < T; t += 2 * G::TW) {
+        float2 y0[D], y1[D];
+        float m0 = 1.f, m1 = 1.f;
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                y0[d] = ch[d][(size_t)t * F];
+                y1[d] = ch[d][(size_t)(t + G::TW) * F];
+            }
+            if (mrow) {
+                m0 = mrow[(size_t)t * mstride];
+                m1 = mrow[(size_t)(t + G::TW) * mstride];
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y0[d] = y1[d] = make_float2(0.f, 0.f);
+        }
+        point(y0, m0, t);
+        point(y1, m1, t + G::TW);
+    }
+    for (; t < T; t += G::TW) {
         float2 y[D];
         float m = 1.f;
         if (active) {
@@ -99,12 +147,11 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
 #pragma unroll
             for (int d = 0; d < D; ++d) y[d] = make_float2(0.f, 0.f);
         }
-        const float wa = m * m, wb = mrow ? (1.f - m) * (1.f - m) : 0.f;
-        PairAcc<D, PART, 0>::run(y, wa, wb, ps, pn);
+        point(y, m, t);
     }
 }
 
-template <int D>
+template <int D, bool ZF>
 __global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs a) {
     using G = ScmGeom<D>;
     extern __shared__ float2 red[];  // [NPART][NPP][2][32]
@@ -121,14 +168,14 @@ __global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs
     for (int q = 0; q < G::NPP; ++q) ps[q] = pn[q] = make_float2(0.f, 0.f);
 
     switch (part) {  // warp-uniform: keeps the (i, j) of every accumulator compile-time
-        case 0: scm_accumulate<D, 0>(a, grp, fc, active, tw, ps, pn); break;
-        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0)>(a, grp, fc, active, tw, ps, pn); break;
-        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0)>(a, grp, fc, active, tw, ps, pn); break;
+        case 0: scm_accumulate<D, 0, ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
     }
 
     // reduce the TW time-ways in fixed order: way w adds into way 0 through shared memory
@@ -180,11 +227,11 @@ __global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs
     }
 }
 
-template <int D>
-static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
+template <int D, bool ZF>
+static cudaError_t launch_dz(const ScmArgs& a, cudaStream_t st) {
     using G = ScmGeom<D>;
     const size_t smem = (size_t)G::NPART * G::NPP * 2 * 32 * sizeof(float2);
-    auto kern = masked_scm_kernel<D>;
+    auto kern = masked_scm_kernel<D, ZF>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -192,6 +239,15 @@ static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
     dim3 grid((a.in.F + 31) / 32, a.in.n_grp);
     kern<<<grid, G::THREADS, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
+    if (a.W1 != nullptr) {
+        if (D > 8) return cudaErrorInvalidValue;
+        return launch_dz<(D > 8 ? 1 : D), true>(a, st);
+    }
+    return launch_dz<D, false>(a, st);
 }
 
 cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st) {

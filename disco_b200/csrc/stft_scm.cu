@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
             const uint32_t ph = (it >> 1) & 1;
             const float* sm = samp + s * SAMP;
             float2* job = spec + s * G::SPEC + (size_t)w * NB * ROWP;
-            float2 v[NB][RA];
             mbar_wait(&samp_full[s], ph);
             {
                 const int s0 = t0 * H - H;
@@ -275,46 +274,41 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                     named_bar_sync(1, 32 * G::FFT_WARPS);
                 }
             }
-            if (nfr == TT && c_valid == C && (C % 2 == 0)) {     // full tile, all channels: no predication
-#pragma unroll
-                for (int q = 0; q < NB; ++q) {
-                    const int item = w * NB + q;
-                    const int tl = item / P, pr = item % P;
-                    const float* xa = sm + (2 * pr) * (TT + 1) * H + tl * H + lane;
-                    const float* xb = xa + (TT + 1) * H;
-#pragma unroll
-                    for (int j = 0; j < RA; ++j) v[q][j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < NB; ++q) {
-                    const int item = w * NB + q;
-                    const int tl = item / P, pr = item % P;
-                    const int ca = 2 * pr, cb = 2 * pr + 1;
-                    const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
-                    const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
-                    if (tl < nfr && cb < c_valid) {
-#pragma unroll
-                        for (int j = 0; j < RA; ++j)
-                            v[q][j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
-                    } else if (tl < nfr && ca < c_valid) {
-#pragma unroll
-                        for (int j = 0; j < RA; ++j) v[q][j] = make_float2(xa[32 * j] * win[j], 0.f);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < RA; ++j) v[q][j] = make_float2(0.f, 0.f);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&samp_empty[s]);       // samples are in registers now
             mbar_wait(&spec_empty[s], ph ^ 1);                // spectrum stage s free (tile it-2 consumed)
+            // inter-pass twiddles W_N^(lane k1): fetched once per job, ahead of the butterflies
+            constexpr bool TWREG = (RA <= 16);
+            float2 twr[TWREG ? RA : 1];
+            if (TWREG) {
+#pragma unroll
+                for (int k1 = 1; k1 < RA; ++k1) twr[k1] = tw[k1 * 32 + lane];
+            }
+            const bool full = (nfr == TT && c_valid == C && (C % 2 == 0));
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
-                dft_reg<RA, false>(v[q]);
+                const int item = w * NB + q;
+                const int tl = item / P, pr = item % P;
+                const int ca = 2 * pr, cb = 2 * pr + 1;
+                const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
+                const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
+                float2 v[RA];
+                if (full || (tl < nfr && cb < c_valid)) {
+#pragma unroll
+                    for (int j = 0; j < RA; ++j) v[j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
+                } else if (tl < nfr && ca < c_valid) {
+#pragma unroll
+                    for (int j = 0; j < RA; ++j) v[j] = make_float2(xa[32 * j] * win[j], 0.f);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RA; ++j) v[j] = make_float2(0.f, 0.f);
+                }
+                if (q == NB - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&samp_empty[s]);   // all samples of this job are in registers
+                }
+                dft_reg<RA, false>(v);
 #pragma unroll
                 for (int k1 = 0; k1 < RA; ++k1) {
-                    const float2 val = (k1 == 0) ? v[q][0] : cmul(v[q][k1], tw[k1 * 32 + lane]);
+                    const float2 val = (k1 == 0) ? v[0] : cmul(v[k1], TWREG ? twr[k1] : tw[k1 * 32 + lane]);
                     job[(q * RA + k1) * 33 + lane] = val;      // scratch [32 rows][33]: conflict-free both ways
                 }
             }
@@ -398,54 +392,46 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
     }
 }
 
-// Reduce the (group, CTA) segment partials in fixed order, scale by 1/T, expand to full Hermitian
+// Reduce the (group, CTA) segment partials in fixed slot order, scale by 1/T, expand to full Hermitian
 // matrices Rss, Rnn [n_grp][F][C][C] complex64 (R[i][j] = mean_t a_i conj(a_j), np.outer convention).
-// One thread per (group, matrix, Hermitian pair, bin): bins are the fastest index so the partial
-// reads are coalesced; the work is tiny, the point is to expose enough loads to hide their latency.
-__global__ void scm_finalize_kernel(const float* __restrict__ part, float2* __restrict__ Rss,
-                                    float2* __restrict__ Rnn, int n_grp, int slots_per_grp, int tiles_per_grp,
-                                    int n_cta, int C, int F, float inv_T) {
-    const int npair = C * (C + 1) / 2;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_total = (long long)n_grp * 2 * npair * F;
-    if (idx >= n_total) return;
-    const int f = (int)(idx % F);
-    long long r = idx / F;
-    const int pr = (int)(r % npair);
-    r /= npair;
-    const int which = (int)(r % 2), g = (int)(r / 2);
-    // pair index -> (i, j): diagonals first (pr < C), then the strict upper triangle row-major
-    int i, j;
-    if (pr < C) {
-        i = j = pr;
-    } else {
-        int o = pr - C;
-        i = 0;
-        int n = C - 1;
-        while (o >= n) {
-            o -= n;
-            --n;
-            ++i;
-        }
-        j = i + 1 + o;
-    }
+// One block per group, one thread per bin: all 2 C^2 * n_slot loads of a thread are independent
+// (coalesced over bins), so the kernel costs about one memory round trip.
+template <int C>
+__global__ void __launch_bounds__(288) scm_finalize_kernel(const float* __restrict__ part, float2* __restrict__ Rss,
+                                                           float2* __restrict__ Rnn, int n_grp, int slots_per_grp,
+                                                           int tiles_per_grp, int n_cta, int F, float inv_T) {
+    constexpr int NACC = 2 * C * C;
+    const int g = blockIdx.x;
     const long long total = (long long)n_grp * tiles_per_grp;
     const int b_first = cta_of_tile((long long)g * tiles_per_grp, total, n_cta);
-    const int b_last = cta_of_tile((long long)(g + 1) * tiles_per_grp - 1, total, n_cta);
-    const int n_slot = b_last - b_first + 1;
-    const int nacc = 2 * C * C, base = which * C * C;
-    const int a_re = (i == j) ? i : C + 2 * (pr - C);
-    float re = 0.f, im = 0.f;
-    for (int sl = 0; sl < n_slot; ++sl) {
-        const float* q = part + (((size_t)g * slots_per_grp + sl) * nacc + base) * F + f;
-        re += q[(size_t)a_re * F];
-        if (i != j) im += q[(size_t)(a_re + 1) * F];
+    const int n_slot = cta_of_tile((long long)(g + 1) * tiles_per_grp - 1, total, n_cta) - b_first + 1;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const float* base = part + (size_t)g * slots_per_grp * NACC * F + f;
+        float acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+        for (int sl = 0; sl < n_slot; ++sl) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] += __ldg(base + ((size_t)sl * NACC + a) * F);
+        }
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            float2* R = (which == 0 ? Rss : Rnn) + ((size_t)g * F + f) * C * C;
+            const float* q = acc + which * C * C;
+            int o = 0;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                R[i * C + i] = make_float2(q[i] * inv_T, 0.f);
+#pragma unroll
+                for (int j = i + 1; j < C; ++j) {
+                    const float re = q[C + 2 * o] * inv_T, im = q[C + 2 * o + 1] * inv_T;
+                    R[i * C + j] = make_float2(re, im);
+                    R[j * C + i] = make_float2(re, -im);
+                    ++o;
+                }
+            }
+        }
     }
-    re *= inv_T;
-    im *= inv_T;
-    float2* R = (which == 0 ? Rss : Rnn) + ((size_t)g * F + f) * C * C;
-    R[i * C + j] = make_float2(re, im);
-    if (i != j) R[j * C + i] = make_float2(re, -im);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -504,9 +490,14 @@ cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool
 
 cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int slots_per_grp,
                                 int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st) {
-    const long long total = (long long)n_grp * C * (C + 1) * F;   // 2 matrices x C(C+1)/2 pairs x F bins
-    scm_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp,
-                                                                        tiles_per_grp, n_cta, C, F, 1.0f / (float)T);
+    const float inv_T = 1.0f / (float)T;
+    switch (C) {
+        case 1: scm_finalize_kernel<1><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
+        case 2: scm_finalize_kernel<2><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
+        case 3: scm_finalize_kernel<3><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
+        case 4: scm_finalize_kernel<4><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

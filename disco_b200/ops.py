@@ -140,6 +140,31 @@ def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
     return Rss, Rnn
 
 
+def filter_sum_scm(W1, Y, mask, ref=0, n_fft=512, mask_layout="TF"):
+    """Single-node groups (no exchange): z = w1^H y, zn = y[ref] - z AND the masked SCMs of Y under `mask`
+    in one pass over Y.  W1 [..., F, C], Y [..., C, T, F], mask [..., T, F] (or [..., F, T]).
+    Returns z, zn [..., T, F], Rss, Rnn [..., F, C, C]."""
+    _need(W1, torch.complex64, "W1")
+    _need(Y, torch.complex64, "Y")
+    _need(mask, torch.float32, "mask")
+    C, T, F = Y.shape[-3:]
+    lead = Y.shape[:-3]
+    G = Y.numel() // (C * T * F)
+    lay = _layout(mask_layout)
+    if tuple(W1.shape) != tuple(lead) + (F, C):
+        raise ValueError("W1 shape %s, expected %s" % (tuple(W1.shape), tuple(lead) + (F, C)))
+    want = tuple(lead) + ((T, F) if lay == TF else (F, T))
+    if tuple(mask.shape) != want:
+        raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
+    z = torch.empty(lead + (T, F), dtype=torch.complex64, device=Y.device)
+    zn = torch.empty_like(z)
+    Rss = torch.empty(lead + (F, C, C), dtype=torch.complex64, device=Y.device)
+    Rnn = torch.empty_like(Rss)
+    _lib.check(_lib.load().disco_filter_sum_scm(_ptr(W1), _ptr(Y), _ptr(mask), lay, _ptr(z), _ptr(zn), int(ref),
+                                                _ptr(Rss), _ptr(Rnn), G, C, T, n_fft, _stream()))
+    return z, zn, Rss, Rnn
+
+
 def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
     """Batched intern_filter (reference internal_formulas.py:31-81).  Rss, Rnn [..., D, D] complex64
     -> W [..., D], t1 [..., D] complex64.  rank 'full'/'Full'/None -> all eigenpairs."""

@@ -42,10 +42,12 @@ def _bcast_mask(X, m, one_minus):
     return out
 
 
-def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mic=0, oracle_sn=None):
+def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mic=0, oracle_sn=None,
+                apply_filter=True):
     """y [B, K, C, L] float32, mask_z [B, K, T, F] float32 (frame-major).
     Returns dict: Y [B,K,C,T,F], z_y, zn [B,K,T,F], W1 [B,K,F,C], R_ss, R_nn.
-    oracle_sn = (S, N) spectra replaces the masked estimates in the SCMs ('use_oracle_*', tango.py:343-345)."""
+    oracle_sn = (S, N) spectra replaces the masked estimates in the SCMs ('use_oracle_*', tango.py:343-345).
+    apply_filter=False leaves z_y / zn to a fused later pass (single-node arrays)."""
     B, K, C, L = y.shape
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
     if oracle_sn is None and C <= 4:
@@ -60,7 +62,9 @@ def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mi
             Rss, _ = ops.masked_scm(oracle_sn[0], None, None, n_fft)
             Rnn, _ = ops.masked_scm(oracle_sn[1], None, None, n_fft)
     W1, _ = ops.mwf_solve(Rss, Rnn, mu, filter_type, rank)
-    z_y, zn = ops.filter_sum(W1, Y, None, conj=True, ref=ref_mic, n_fft=n_fft)
+    z_y = zn = None
+    if apply_filter:
+        z_y, zn = ops.filter_sum(W1, Y, None, conj=True, ref=ref_mic, n_fft=n_fft)
     return {"Y": Y, "z_y": z_y, "zn": zn, "W1": W1, "R_ss": Rss, "R_nn": Rnn}
 
 
@@ -119,8 +123,14 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
             mask_w = mask_z
     # ---- step 1
     osn = (S, N) if "use_oracle_" in mask_for_z else None
-    st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn)
+    # single-node arrays: no exchange, so the step-1 filter-and-sum and the step-2 SCM share one pass over Y
+    fuse_mid = (K == 1 and mask_for_z == "local" and C <= 8)
+    st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn, apply_filter=not fuse_mid)
     Y, z_y, zn, W1 = st1["Y"], st1["z_y"], st1["zn"], st1["W1"]
+    R2 = None
+    if fuse_mid:
+        z_y, zn, Rss2, Rnn2 = ops.filter_sum_scm(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
+        R2 = (Rss2, Rnn2)
     z_s = z_n = None
     if have_sn and (diagnostics or mask_for_z in ("compressed", "use_oracle_zs")):
         z_s = ops.filter_sum(W1, S, None, conj=True, n_fft=n_fft)
@@ -144,7 +154,11 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     else:   # 'previous' and any other string: unmasked z in both statistics (tango.py:428-429)
         z_rs = z_rn = z_y
     # ---- step 2
-    yf, W2 = tango_step2(Y, z_y, mask_w, n_fft, mu, filter_type, rank, out_layout, z_rs=z_rs, z_rn=z_rn)
+    if R2 is not None:
+        W2, _ = ops.mwf_solve(R2[0], R2[1], mu, filter_type, rank)
+        yf = ops.filter_sum(W2, Y, None, conj=True, n_fft=n_fft, out_layout=out_layout)
+    else:
+        yf, W2 = tango_step2(Y, z_y, mask_w, n_fft, mu, filter_type, rank, out_layout, z_rs=z_rs, z_rn=z_rn)
     out = {"yf": yf}
     if have_sn and diagnostics:
         out["sf"] = ops.filter_sum(W2, S, z_s, conj=True, n_fft=n_fft, out_layout=out_layout)

@@ -113,6 +113,15 @@ DISCO_API int disco_tf_mask(const void* S, const void* N, float* M, size_t n_ele
 DISCO_API int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_layout, void* Rss, void* Rnn,
                      int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, void* stream);
 
+/* ---- fused step-1 filter-and-sum + step-2 masked SCM for single-node groups (K = 1) ----------------
+ * One pass over Y instead of two: z = w1^H y and zn = y[ref] - z (reference tango.py:369-376) are
+ * written while the step-2 SCMs under `mask` (= mask_w, tango.py:431-440 with no exchanged signals,
+ * D = C) are accumulated.  W1 [n_grp][F][C]; z_out, zn_out [n_grp][T][F] (zn_out may be NULL);
+ * Rss, Rnn [n_grp][F][C][C]. */
+DISCO_API int disco_filter_sum_scm(const void* W1, const void* Y, const float* mask, int mask_layout, void* z_out,
+                                   void* zn_out, int ref, void* Rss, void* Rnn, int n_grp, int C, int T, int n_fft,
+                                   void* stream);
+
 /* ---- per-bin MWF solve ---------------------------------------------------------------------------
  * Replaces intern_filter(Rxx, Rnn, mu, type, rank) (reference internal_formulas.py:31-81) for
  * n_mat matrices: Rss, Rnn [n_mat][D][D] complex64 -> W [n_mat][D], T1 [n_mat][D] complex64

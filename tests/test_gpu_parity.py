@@ -202,6 +202,22 @@ def test_independent_nodes_without_exchange(dev):
             assert rel_l2(_np(res)[b, k], Y[b, k, 1] - ref) < 1e-6
 
 
+@pytest.mark.parametrize("C", [1, 2, 4, 8])
+def test_fused_filter_sum_scm_equals_separate_ops(dev, C):
+    """filter_sum (step 1) + masked_scm (step 2) in one pass == the two separate kernels, bit for bit."""
+    from disco_b200 import ops
+    rng = np.random.default_rng(C)
+    B, K, T, F = 3, 1, 77, 257
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, W = torch.from_numpy(cplx(B, K, C, T, F)).to(dev), torch.from_numpy(cplx(B, K, F, C)).to(dev)
+    m = torch.from_numpy(rng.uniform(size=(B, K, T, F)).astype(np.float32)).to(dev)
+    z, zn, Rss, Rnn = ops.filter_sum_scm(W, Y, m, ref=C - 1)
+    z2, zn2 = ops.filter_sum(W, Y, None, conj=True, ref=C - 1)
+    Rss2, Rnn2 = ops.masked_scm(Y, m, None)
+    assert torch.equal(Rss, Rss2) and torch.equal(Rnn, Rnn2)
+    assert rel_l2(_np(z), _np(z2)) < 1e-6 and rel_l2(_np(zn), _np(zn2)) < 1e-6
+
+
 def test_tf_mask_kats(dev):
     from disco_b200 import ops
     g = load_golden("helpers_kat")
