@@ -42,6 +42,20 @@ def _bcast_mask(X, m, one_minus):
     return out
 
 
+def _ivad_mask(s_ref, n_fft):
+    """'ivad' masks (tango.py:216-221): the per-sample energy VAD of the clean reference channel,
+    taken every hop and spread over all bins.  s_ref [B, K, L] -> [B, K, T, F] float32 (0/1)."""
+    from .compat.sigproc_utils import vad_oracle_batch_device
+    B, K, L = s_ref.shape
+    hop, F, T = n_fft // 2, n_fft // 2 + 1, ops.n_frames(L, n_fft)
+    out = torch.zeros((B, K, T, F), dtype=torch.float32, device=s_ref.device)
+    for b in range(B):
+        for k in range(K):
+            vad = vad_oracle_batch_device(s_ref[b, k], win_len=n_fft, win_hop=hop)[::hop]
+            out[b, k, :vad.numel(), :] = vad.to(torch.float32)[:, None]
+    return out
+
+
 def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mic=0, oracle_sn=None,
                 apply_filter=True):
     """y [B, K, C, L] float32, mask_z [B, K, T, F] float32 (frame-major).
@@ -110,13 +124,18 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     # ---- masks
     if oracle:
         for v in vads:
-            if not _is_oracle_type(v):
+            if not (_is_oracle_type(v) or v == "ivad"):
                 raise ValueError("Unknown value for `mask_type`")      # tango.py:223
-        mask_z = ops.tf_mask(_ref_plane(S, ref_mic), _ref_plane(N, ref_mic), vads[0])
+
+        def oracle_mask(kind, ch):
+            if kind == "ivad":                                          # tango.py:216-221
+                return _ivad_mask(s[:, :, ch], n_fft)
+            return ops.tf_mask(_ref_plane(S, ch), _ref_plane(N, ch), kind)
+        mask_z = oracle_mask(vads[0], ref_mic)
         if vads[1] == vads[0] and ref_mic == 0:
             mask_w = mask_z
         else:
-            mask_w = ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), vads[1])   # channel 0, tango.py:391
+            mask_w = oracle_mask(vads[1], 0)                            # channel 0, tango.py:391
     else:
         mask_z, mask_w = masks
         if mask_w is None:
@@ -219,11 +238,14 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
     else:
         res = _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask)
     is_bool = [masks is None and "ibm" in v for v in vads]
+    is_f64 = [masks is None and v == "ivad" for v in vads]       # the reference's VAD masks are float64
     out = []
     for nm in OUTPUT_NAMES:
         arr = res[nm]
         if nm == "masks_z" and is_bool[0] or nm == "mask_w" and is_bool[1]:
             arr = arr.astype(bool)
+        if nm == "masks_z" and is_f64[0] or nm == "mask_w" and is_f64[1]:
+            arr = arr.astype(np.float64)
         out.append([arr[k] for k in range(K)])
     return tuple(out)
 
@@ -249,8 +271,10 @@ def _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, ran
         yd, sd, nd = _to_dev(y, nodes, dev), _to_dev(s, nodes, dev), _to_dev(n, nodes, dev)
         S, N = ops.stft(sd, n_fft), ops.stft(nd, n_fft)
         if masks is None:
-            mz = ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), vads[0])
-            mw = mz if vads[1] == vads[0] else ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), vads[1])
+            om = lambda kind: _ivad_mask(sd[:, :, 0], n_fft) if kind == "ivad" else \
+                ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), kind)
+            mz = om(vads[0])
+            mw = mz if vads[1] == vads[0] else om(vads[1])
         else:
             mz, mw = to_mask(masks[0], nodes), to_mask(masks[1], nodes)
         st1 = tango_step1(yd, mz, n_fft, mu, filter_type, rank, 0)

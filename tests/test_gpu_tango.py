@@ -37,7 +37,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-GPU_CASES = [c for c in sorted(TANGO_CASES) if "ivad" not in c]
+GPU_CASES = sorted(TANGO_CASES)
 # Binary masks make R_nn exactly singular in bins where the mask is 1 in every frame; the reference
 # then depends on LAPACK returning inf/NaN generalised eigenvalues (internal_formulas.py:59-62), which
 # no other arithmetic can reproduce.  For those cases only the masks are compared.
