@@ -44,18 +44,48 @@ __global__ void __launch_bounds__(256) filter_sum_kernel(FilterArgs a, int frame
     }
     const float2* refch = cat_channel_fs(a.in, grp, a.ref) + fc;
 
+    // Software pipeline (small D): the 4 frames this warp owns in the NEXT 32-frame tile are loaded
+    // before the current ones are consumed, keeping 4 D loads per thread in flight.
+    constexpr bool PF = (D <= 5);
+    float2 nx[PF ? 4 : 1][D];
+    float2 nr[PF ? 4 : 1];
+    auto fetch = [&](int t0) {
+        if (PF) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + wrp * 4 + i;
+                const bool ok = t < t_end;
+#pragma unroll
+                for (int d = 0; d < D; ++d) nx[i][d] = ok ? ch[d][(size_t)t * F] : make_float2(0.f, 0.f);
+                nr[i] = (ok && a.resid) ? refch[(size_t)t * F] : make_float2(0.f, 0.f);
+            }
+        }
+    };
+    fetch(t_begin);
     for (int t0 = t_begin; t0 < t_end; t0 += 32) {
+        float2 cx[4][D], cr[4];
+        if (PF) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) cx[i][d] = nx[i][d];
+                cr[i] = nr[i];
+            }
+            fetch(t0 + 32);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int tl = wrp * 4 + i, t = t0 + tl;
             float2 acc = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
             if (t < t_end) {
-                float2 x[D];
+                if (!PF) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) x[d] = ch[d][(size_t)t * F];
+                    for (int d = 0; d < D; ++d) cx[i][d] = ch[d][(size_t)t * F];
+                    cr[i] = a.resid ? refch[(size_t)t * F] : make_float2(0.f, 0.f);
+                }
 #pragma unroll
-                for (int d = 0; d < D; ++d) acc = cadd(acc, cmul(w[d], x[d]));
-                if (a.resid) r = csub(refch[(size_t)t * F], acc);
+                for (int d = 0; d < D; ++d) acc = cadd(acc, cmul(w[d], cx[i][d]));
+                if (a.resid) r = csub(cr[i], acc);
                 if (!a.out_ft && active) {
                     a.out[((size_t)grp * T + t) * F + f] = acc;
                     if (a.resid) a.resid[((size_t)grp * T + t) * F + f] = r;

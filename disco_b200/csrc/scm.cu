@@ -114,40 +114,32 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
             }
         }
     };
-    int t = tw;
-    // two frames per iteration: twice the loads in flight per thread
-    for (; t + G::TW < T; t += 2 * G::TW) {
+    // Software pipeline over time: the loads of the NEXT pair of frames are issued before the
+    // current pair is consumed, so every thread keeps 2 D loads in flight while it computes.
+    auto load2 = [&](int t, float2 (&ya)[D], float2 (&yb)[D], float& ma, float& mb) {
+        const bool ha = active && t < T, hb = active && (t + G::TW) < T;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            ya[d] = ha ? ch[d][(size_t)t * F] : make_float2(0.f, 0.f);
+            yb[d] = hb ? ch[d][(size_t)(t + G::TW) * F] : make_float2(0.f, 0.f);
+        }
+        ma = (ha && mrow) ? mrow[(size_t)t * mstride] : 1.f;
+        mb = (hb && mrow) ? mrow[(size_t)(t + G::TW) * mstride] : 1.f;
+    };
+    float2 na[D], nb[D];
+    float nma, nmb;
+    load2(tw, na, nb, nma, nmb);
+    for (int t = tw; t < T; t += 2 * G::TW) {
         float2 y0[D], y1[D];
-        float m0 = 1.f, m1 = 1.f;
-        if (active) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                y0[d] = ch[d][(size_t)t * F];
-                y1[d] = ch[d][(size_t)(t + G::TW) * F];
-            }
-            if (mrow) {
-                m0 = mrow[(size_t)t * mstride];
-                m1 = mrow[(size_t)(t + G::TW) * mstride];
-            }
-        } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) y0[d] = y1[d] = make_float2(0.f, 0.f);
+        for (int d = 0; d < D; ++d) {
+            y0[d] = na[d];
+            y1[d] = nb[d];
         }
+        const float m0 = nma, m1 = nmb;
+        load2(t + 2 * G::TW, na, nb, nma, nmb);       // next iteration's loads (all-zero past the end)
         point(y0, m0, t);
-        point(y1, m1, t + G::TW);
-    }
-    for (; t < T; t += G::TW) {
-        float2 y[D];
-        float m = 1.f;
-        if (active) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) y[d] = ch[d][(size_t)t * F];
-            if (mrow) m = mrow[(size_t)t * mstride];
-        } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) y[d] = make_float2(0.f, 0.f);
-        }
-        point(y, m, t);
+        if (t + G::TW < T) point(y1, m1, t + G::TW);
     }
 }
 

@@ -49,12 +49,13 @@ struct Ld {
 // lower triangle with real positive diagonal.  Pivots are floored at `floor_`.
 template <int D>
 DISCO_DEV void cholesky(cd (&M)[D][Ld<D>::v], double floor_) {
-#pragma unroll 1
+    constexpr int U = (D <= 4) ? D : 1;   // small matrices: fully unrolled, register resident
+#pragma unroll U
     for (int j = 0; j < D; ++j) {
         double d = M[j][j].x;
         for (int k = 0; k < j; ++k) d -= norm2(M[j][k]);
         d = fmax(d, floor_);
-        const double l = sqrt(d), inv = 1.0 / l;
+        const double inv = rsqrt(d), l = d * inv;
         M[j][j] = mk(l, 0.0);
         for (int i = j + 1; i < D; ++i) {
             cd s = M[i][j];
@@ -64,55 +65,79 @@ DISCO_DEV void cholesky(cd (&M)[D][Ld<D>::v], double floor_) {
     }
 }
 
+// One Jacobi rotation annihilating A[p][q] (and A[q][p]); A <- G^H A G, V <- V G.
+// Three expensive float64 operations per rotation (rsqrt, sqrt + div, rsqrt) instead of six.
+template <int D>
+DISCO_DEV void jacobi_rotate(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], int p, int q) {
+    const cd b = A[p][q];
+    const double n2 = norm2(b);
+    if (n2 < 1e-300) return;
+    const double inv_ab = rsqrt(n2), ab = n2 * inv_ab;
+    const cd ph = inv_ab * b;
+    const double d = 0.5 * (A[q][q].x - A[p][p].x);
+    const double t = copysign(ab, d) / (fabs(d) + sqrt(d * d + n2));   // tan of the rotation angle
+    const double c = rsqrt(1.0 + t * t), s = t * c;
+    const cd st = s * ph, stc = conj(st);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {  // A <- A G
+        const cd akp = A[k][p], akq = A[k][q];
+        A[k][p] = c * akp - stc * akq;
+        A[k][q] = st * akp + c * akq;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {  // A <- G^H A
+        const cd apk = A[p][k], aqk = A[q][k];
+        A[p][k] = c * apk - st * aqk;
+        A[q][k] = stc * apk + c * aqk;
+    }
+    A[p][q] = mk(0.0, 0.0);
+    A[q][p] = mk(0.0, 0.0);
+    A[p][p].y = 0.0;
+    A[q][q].y = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {  // V <- V G
+        const cd vkp = V[k][p], vkq = V[k][q];
+        V[k][p] = c * vkp - stc * vkq;
+        V[k][q] = st * vkp + c * vkq;
+    }
+}
+
 // Cyclic Jacobi for a Hermitian matrix A (destroyed); V receives the eigenvectors (columns),
-// lam the eigenvalues (unsorted).
+// lam the eigenvalues (unsorted).  Converged when the off-diagonal energy is below 1e-26 of the
+// total (the inputs carry float32 rounding, ~1e-14 relative energy).  For D <= 4 the (p, q) loops are
+// fully unrolled so that A and V live in registers; larger matrices index local memory.
 template <int D>
 DISCO_DEV void jacobi(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], double (&lam)[D]) {
+#pragma unroll
     for (int i = 0; i < D; ++i)
+#pragma unroll
         for (int j = 0; j < D; ++j) V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
     double tot = 0.0;
+#pragma unroll
     for (int i = 0; i < D; ++i)
+#pragma unroll
         for (int j = 0; j < D; ++j) tot += norm2(A[i][j]);
 #pragma unroll 1
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0;
+#pragma unroll
         for (int p = 0; p < D; ++p)
+#pragma unroll
             for (int q = p + 1; q < D; ++q) off += norm2(A[p][q]);
-        if (off <= 1e-30 * tot) break;
+        if (off <= 1e-26 * tot) break;
+        if constexpr (D <= 4) {
+#pragma unroll
+            for (int p = 0; p < D - 1; ++p)
+#pragma unroll
+                for (int q = p + 1; q < D; ++q) jacobi_rotate<D>(A, V, p, q);
+        } else {
 #pragma unroll 1
-        for (int p = 0; p < D - 1; ++p) {
+            for (int p = 0; p < D - 1; ++p)
 #pragma unroll 1
-            for (int q = p + 1; q < D; ++q) {
-                const cd b = A[p][q];
-                const double ab = sqrt(norm2(b));
-                if (ab < 1e-300) continue;
-                const cd ph = (1.0 / ab) * b;
-                const double tau = (A[q][q].x - A[p][p].x) / (2.0 * ab);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-                const cd st = s * ph, stc = conj(st);
-                for (int k = 0; k < D; ++k) {  // A <- A G
-                    const cd akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - stc * akq;
-                    A[k][q] = st * akp + c * akq;
-                }
-                for (int k = 0; k < D; ++k) {  // A <- G^H A
-                    const cd apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - st * aqk;
-                    A[q][k] = stc * apk + c * aqk;
-                }
-                A[p][q] = mk(0.0, 0.0);
-                A[q][p] = mk(0.0, 0.0);
-                A[p][p].y = 0.0;
-                A[q][q].y = 0.0;
-                for (int k = 0; k < D; ++k) {  // V <- V G
-                    const cd vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - stc * vkq;
-                    V[k][q] = st * vkp + c * vkq;
-                }
-            }
+                for (int q = p + 1; q < D; ++q) jacobi_rotate<D>(A, V, p, q);
         }
     }
+#pragma unroll
     for (int i = 0; i < D; ++i) lam[i] = A[i][i].x;
 }
 
