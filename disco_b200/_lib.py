@@ -29,6 +29,8 @@ SIGNATURES = {
                                  c_int, c_int_p, c_int, c_void_p]),
     "disco_filter_sum_scm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p]),
+    "disco_mwf_solve_workspace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_int, c_int, c_double, c_void_p]),
     "disco_mwf_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
                                 c_void_p]),
     "disco_filter_sum": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -134,12 +134,12 @@ int stft_common(const float* x, const float* mask, int mask_layout, void* Y, voi
     a.slots_per_grp = pl.slots_per_grp;
     cudaStream_t st = (cudaStream_t)stream;
     if (scm) {
-        if (!mask || !Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
+        if (!mask || (!Rss) != (!Rnn)) return fail(DISCO_ERR_INVALID, "null pointer");
         const size_t need = disco_stft_scm_workspace(n_grp, C, length, n_fft);
         if (!workspace || workspace_bytes < need) return fail(DISCO_ERR_WORKSPACE, "workspace too small");
     }
     CU(launch_stft_scm(a, n_fft, C, pl.n_cta, scm, st), "stft_scm launch");
-    if (scm)
+    if (scm && Rss)
         CU(launch_scm_finalize(a.part, (float2*)Rss, (float2*)Rnn, n_grp, pl.slots_per_grp, pl.tiles_per_grp,
                                pl.n_cta, C, n_fft / 2 + 1, T, st),
            "scm_finalize launch");
@@ -257,12 +257,41 @@ int disco_filter_sum_scm(const void* W1, const void* Y, const float* mask, int m
     return 0;
 }
 
+int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp, int C,
+                              int length, int n_fft, int filter_type, int rank, double mu, void* stream) {
+    if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");
+    if (!valid_nfft(n_fft) || n_grp < 1 || C < 1 || C > 4 || !workspace || !W || (!Rss) != (!Rnn))
+        return fail(DISCO_ERR_INVALID, "bad arguments");
+    const int T = disco_n_frames(length, n_fft), F = n_fft / 2 + 1;
+    const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Rss = (const float2*)Rss;
+    a.Rnn = (const float2*)Rnn;
+    a.W = (float2*)W;
+    a.T1 = (float2*)T1;
+    a.n_mat = n_grp * F;
+    a.D = C;
+    a.type = filter_type;
+    a.rank = rank;
+    a.mu = mu;
+    a.part = (const float*)workspace;
+    a.slots_per_grp = pl.slots_per_grp;
+    a.tiles_per_grp = pl.tiles_per_grp;
+    a.n_cta = pl.n_cta;
+    a.F = F;
+    a.inv_T = 1.0f / (float)T;
+    CU(launch_mwf_solve(a, (cudaStream_t)stream), "mwf_solve launch");
+    return 0;
+}
+
 int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
                     int rank, double mu, void* stream) {
     if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");
     if (D < 1 || D > 15) return fail(DISCO_ERR_UNSUPPORTED, "D must be in 1..15");
     if (n_mat < 0 || !Rss || !Rnn || !W) return fail(DISCO_ERR_INVALID, "bad arguments");
     SolveArgs a;
+    memset(&a, 0, sizeof(a));
     a.Rss = (const float2*)Rss;
     a.Rnn = (const float2*)Rnn;
     a.W = (float2*)W;

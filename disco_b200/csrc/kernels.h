@@ -23,6 +23,7 @@ cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int
                                 int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st);
 int stft_tiles_per_grp(int n_fft, int C, int T);
 int stft_slots_per_grp(int n_grp, int tiles_per_grp, int n_cta);
+int stft_cta_of_tile_host(long long i, long long total, int nb);
 
 // Step-2 style input: group g = (utterance b, node k) sees D = C + K - 1 channels:
 // its own C microphone spectra, then the compressed signals z of the other nodes in node
@@ -61,6 +62,11 @@ struct SolveArgs {
     int type;            // 0 gevd, 1 r1-mwf, 2 mwf
     int rank;            // gevd: number of generalised eigenpairs kept; <= 0 or >= D means full
     double mu;
+    // optional: read the matrices straight from the fused STFT+SCM kernel's segment partial sums
+    // (skips scm_finalize); matrix idx = grp * F + f
+    const float* part;   // [n_grp][slots_per_grp][2 D^2][F] or null
+    int slots_per_grp, tiles_per_grp, n_cta, F;
+    float inv_T;
 };
 cudaError_t launch_mwf_solve(const SolveArgs& a, cudaStream_t st);
 

@@ -153,18 +153,71 @@ DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][Ld<D>::v]) {
         }
 }
 
-template <int D, int MINB>
+// Rebuild one Hermitian matrix from the fused STFT+SCM kernel's partial sums: accumulator layout
+// [D diagonals][D(D-1)/2 x (re, im) upper pairs, row-major], slots summed in order, scaled by 1/T
+// (same arithmetic as scm_finalize_kernel, so both routes give bit-identical matrices).
+template <int D>
+DISCO_DEV void load_part(const float* __restrict__ q, int n_slot, size_t slot_stride, int F, float inv_T,
+                         cd (&M)[D][Ld<D>::v]) {
+    float acc[D * D];
+#pragma unroll
+    for (int a = 0; a < D * D; ++a) acc[a] = 0.f;
+    for (int sl = 0; sl < n_slot; ++sl) {
+#pragma unroll
+        for (int a = 0; a < D * D; ++a) acc[a] += __ldg(q + sl * slot_stride + (size_t)a * F);
+    }
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        M[i][i] = mk((double)(acc[i] * inv_T), 0.0);
+#pragma unroll
+        for (int j = i + 1; j < D; ++j) {
+            const cd v = mk((double)(acc[D + 2 * o] * inv_T), (double)(acc[D + 2 * o + 1] * inv_T));
+            M[i][j] = v;
+            M[j][i] = conj(v);
+            ++o;
+        }
+    }
+}
+
+__device__ __forceinline__ int cta_of_tile_dev(long long i, long long total, int nb) {
+    int b = (int)((i * nb) / total);
+    if (b >= nb) b = nb - 1;
+    while (b + 1 < nb && total * (b + 1) / nb <= i) ++b;
+    while (b > 0 && total * b / nb > i) --b;
+    return b;
+}
+
+template <int D, int MINB, bool PART>
 __global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_mat) return;
-    const float2* Rs = a.Rss + (size_t)idx * D * D;
-    const float2* Rn = a.Rnn + (size_t)idx * D * D;
     constexpr int LD = Ld<D>::v;
     cd S[D][LD], Nn[D][LD], V[D][LD];
     cd w[D], t1[D];
     for (int i = 0; i < D; ++i) t1[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);   // e_0 (internal_formulas.py:43)
-    load_herm<D>(Rs, S);
-    load_herm<D>(Rn, Nn);
+    if (PART) {
+        const int g = idx / a.F, f = idx % a.F;
+        const long long total = (long long)(a.n_mat / a.F) * a.tiles_per_grp;
+        const int b_first = cta_of_tile_dev((long long)g * a.tiles_per_grp, total, a.n_cta);
+        const int n_slot = cta_of_tile_dev((long long)(g + 1) * a.tiles_per_grp - 1, total, a.n_cta) - b_first + 1;
+        const size_t slot_stride = (size_t)2 * D * D * a.F;
+        const float* q = a.part + (size_t)g * a.slots_per_grp * slot_stride + f;
+        load_part<D>(q, n_slot, slot_stride, a.F, a.inv_T, S);
+        load_part<D>(q + (size_t)D * D * a.F, n_slot, slot_stride, a.F, a.inv_T, Nn);
+        if (a.Rss) {   // optionally also materialise the matrices (API output of the fused op)
+            float2* Rs = const_cast<float2*>(a.Rss) + (size_t)idx * D * D;
+            float2* Rn = const_cast<float2*>(a.Rnn) + (size_t)idx * D * D;
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) {
+                    Rs[i * D + j] = make_float2((float)S[i][j].x, (float)S[i][j].y);
+                    Rn[i * D + j] = make_float2((float)Nn[i][j].x, (float)Nn[i][j].y);
+                }
+        }
+    } else {
+        load_herm<D>(a.Rss + (size_t)idx * D * D, S);
+        load_herm<D>(a.Rnn + (size_t)idx * D * D, Nn);
+    }
     double trn = 0.0, trs = 0.0;
     for (int i = 0; i < D; ++i) trn += Nn[i][i].x, trs += S[i][i].x;
 
@@ -276,11 +329,12 @@ __global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
 
 template <int D>
 static cudaError_t launch_d(const SolveArgs& a, cudaStream_t st) {
-    static const bool alt = getenv("DISCO_SOLVE_ALT") != nullptr;   // debug: second register budget
-    if (alt && D == 16)
-        mwf_solve_kernel<D, (D == 16 ? 8 : 1)><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
-    else
-        mwf_solve_kernel<D, 1><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    if (a.part != nullptr) {
+        if (D > 4) return cudaErrorInvalidValue;
+        mwf_solve_kernel<(D > 4 ? 1 : D), 1, true><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    } else {
+        mwf_solve_kernel<D, 1, false><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

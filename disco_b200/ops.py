@@ -63,9 +63,11 @@ def stft(x, n_fft=512):
     return Y
 
 
-def stft_scm(x, mask, n_fft=512, mask_layout="TF"):
+def stft_scm(x, mask, n_fft=512, mask_layout="TF", keep_partials=False):
     """Fused STFT + masked SCM.  x [G, C, L] float32, mask [G, T, F] (or [G, F, T]) float32
-    -> Y [G, C, T, F] complex64, Rss, Rnn [G, F, C, C] complex64."""
+    -> Y [G, C, T, F] complex64, Rss, Rnn [G, F, C, C] complex64.
+    keep_partials=True returns (Y, workspace) instead: the SCMs stay as per-segment partial sums that
+    mwf_solve_workspace() consumes directly (one launch fewer)."""
     _need(x, torch.float32, "x")
     _need(mask, torch.float32, "mask")
     if x.dim() != 3:
@@ -78,13 +80,35 @@ def stft_scm(x, mask, n_fft=512, mask_layout="TF"):
         raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
     lib = _lib.load()
     Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
-    Rss = torch.empty((G, F, C, C), dtype=torch.complex64, device=x.device)
-    Rnn = torch.empty_like(Rss)
     ws_bytes = lib.disco_stft_scm_workspace(G, C, L, n_fft)
     ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
+    if keep_partials:
+        _lib.check(lib.disco_stft_scm(_ptr(x), _ptr(mask), lay, _ptr(Y), None, None, G, C, L, n_fft,
+                                      _ptr(ws), ws_bytes, _stream()))
+        return Y, ws
+    Rss = torch.empty((G, F, C, C), dtype=torch.complex64, device=x.device)
+    Rnn = torch.empty_like(Rss)
     _lib.check(lib.disco_stft_scm(_ptr(x), _ptr(mask), lay, _ptr(Y), _ptr(Rss), _ptr(Rnn), G, C, L, n_fft,
                                   _ptr(ws), ws_bytes, _stream()))
     return Y, Rss, Rnn
+
+
+def mwf_solve_workspace(ws, G, C, L, n_fft=512, mu=1.0, type="gevd", rank=1, want_scm=False):
+    """mwf_solve on the SCMs a preceding stft_scm(..., keep_partials=True) left in `ws`.
+    Returns W, t1 [G, F, C] (and Rss, Rnn [G, F, C, C] when want_scm)."""
+    if type not in FILTER_TYPES:
+        raise AttributeError("Unknown filter reference")
+    F = n_fft // 2 + 1
+    r = 0 if rank in ("full", "Full", None) else int(rank)
+    W = torch.empty((G, F, C), dtype=torch.complex64, device=ws.device)
+    T1 = torch.empty_like(W)
+    Rss = Rnn = None
+    if want_scm:
+        Rss = torch.empty((G, F, C, C), dtype=torch.complex64, device=ws.device)
+        Rnn = torch.empty_like(Rss)
+    _lib.check(_lib.load().disco_mwf_solve_workspace(_ptr(ws), _ptr(W), _ptr(T1), _ptr(Rss), _ptr(Rnn), G, C, L, n_fft,
+                                                     FILTER_TYPES[type], r, float(mu), _stream()))
+    return (W, T1, Rss, Rnn) if want_scm else (W, T1)
 
 
 def tf_mask(S, N, type="irm1", bin_thr=0.0):

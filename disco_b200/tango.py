@@ -65,9 +65,15 @@ def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mi
     B, K, C, L = y.shape
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
     if oracle_sn is None and C <= 4:
-        Y, Rss, Rnn = ops.stft_scm(y.view(B * K, C, L), mask_z.view(B * K, T, F), n_fft)
+        # fused STFT + SCM; the solve reads the per-segment partial sums directly (no finalize launch)
+        Y, ws = ops.stft_scm(y.view(B * K, C, L), mask_z.view(B * K, T, F), n_fft, keep_partials=True)
         Y = Y.view(B, K, C, T, F)
-        Rss, Rnn = Rss.view(B, K, F, C, C), Rnn.view(B, K, F, C, C)
+        W1, _ = ops.mwf_solve_workspace(ws, B * K, C, L, n_fft, mu, filter_type, rank)
+        W1 = W1.view(B, K, F, C)
+        z_y = zn = None
+        if apply_filter:
+            z_y, zn = ops.filter_sum(W1, Y, None, conj=True, ref=ref_mic, n_fft=n_fft)
+        return {"Y": Y, "z_y": z_y, "zn": zn, "W1": W1, "R_ss": None, "R_nn": None}
     else:
         Y = ops.stft(y, n_fft)
         if oracle_sn is None:

@@ -88,7 +88,9 @@ DISCO_API int disco_stft(const float* x, void* Y, int n_sig, int length, int n_f
  *   Y    [n_grp][C][T][F] complex64                (output, materialised: step 2 re-reads it)
  *   Rss, Rnn [n_grp][F][C][C] complex64            (outputs)
  * C <= 4 in this version (larger arrays: disco_stft + disco_masked_scm).
- * workspace: disco_stft_scm_workspace() bytes of device scratch. */
+ * workspace: disco_stft_scm_workspace() bytes of device scratch.  Rss = Rnn = NULL skips the small
+ * reduction launch that materialises the matrices: the per-segment partial sums stay in `workspace`
+ * and disco_mwf_solve_workspace() consumes them directly (same summation order, identical result). */
 DISCO_API size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft);
 DISCO_API int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn,
                    int n_grp, int C, int length, int n_fft, void* workspace, size_t workspace_bytes,
@@ -130,6 +132,13 @@ DISCO_API int disco_filter_sum_scm(const void* W1, const void* Y, const float* m
  * until that is resolved).  Arithmetic in float64. */
 DISCO_API int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
                     int rank, double mu, void* stream);
+
+/* Same solve, reading the SCMs from the workspace a preceding disco_stft_scm(n_grp, C, length, n_fft) call
+ * left behind (matrix index = group * F + bin; W, T1 [n_grp][F][C]).  Rss / Rnn non-NULL: also write the
+ * matrices ([n_grp][F][C][C]). */
+DISCO_API int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp,
+                                        int C, int length, int n_fft, int filter_type, int rank, double mu,
+                                        void* stream);
 
 /* ---- filter-and-sum ------------------------------------------------------------------------------
  * Replaces np.inner(conj(w), x[:, f, t]) (conj_w = 1) / np.inner(t1, x[:, f, t]) (conj_w = 0) over

@@ -237,3 +237,20 @@ def test_requires_cuda_tensors(dev):
     from disco_b200 import ops
     with pytest.raises(TypeError):
         ops.stft(torch.zeros(1, 4000))           # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("G,C", [(3, 4), (70, 2), (5, 1)])
+def test_solve_from_workspace_equals_two_step_route(dev, G, C):
+    """stft_scm(keep_partials) + mwf_solve_workspace == stft_scm + mwf_solve, bit for bit."""
+    from disco_b200 import ops
+    rng = np.random.default_rng(G)
+    L = 9000
+    x = torch.from_numpy(rng.standard_normal((G, C, L)).astype(np.float32)).to(dev)
+    T, F = 1 + L // 256, 257
+    m = torch.from_numpy(rng.uniform(0.05, 0.95, size=(G, T, F)).astype(np.float32)).to(dev)
+    Y1, Rss, Rnn = ops.stft_scm(x, m)
+    W1, t1 = ops.mwf_solve(Rss, Rnn, 1.0, "gevd", 1)
+    Y2, ws = ops.stft_scm(x, m, keep_partials=True)
+    W2, t2, Rss2, Rnn2 = ops.mwf_solve_workspace(ws, G, C, L, want_scm=True)
+    assert torch.equal(Y1, Y2) and torch.equal(Rss, Rss2) and torch.equal(Rnn, Rnn2)
+    assert torch.equal(W1, W2) and torch.equal(t1, t2)
