@@ -1,6 +1,7 @@
 // C ABI of libdisco_b200.so (declared in include/disco_b200.h): argument checking, per-device
 // constant tables, launch-geometry choices.  No torch types cross this boundary.
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -130,6 +131,10 @@ int stft_common(const float* x, const float* mask, int mask_layout, void* Y, voi
     a.T = T;
     a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
     a.use_tma = (length % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    {
+        static const int dbg = getenv("DISCO_DBG") ? atoi(getenv("DISCO_DBG")) : 0;
+        a.dbg = dbg;
+    }
     const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
     a.slots_per_grp = pl.slots_per_grp;
     cudaStream_t st = (cudaStream_t)stream;

@@ -16,6 +16,7 @@ struct StftArgs {
     int slots_per_grp;
     int mask_ft;
     int use_tma;
+    int dbg;                // profiling experiments only (DISCO_DBG env): 1 no Y stores, 2 no SCM math, 4 no FFT math
 };
 
 cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool scm, cudaStream_t st);

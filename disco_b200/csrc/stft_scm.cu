@@ -189,9 +189,21 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                                     (uint32_t)((TT + 1) * H * sizeof(float)), &samp_full[s]);
                 }
             } else {
-                // edge tile (reflect padding / short tail): the FFT warps fill the stage themselves
-                // with all their threads; the loader only hands the free buffer over.
-                if (lane == 0) mbar_arrive(&samp_full[s]);
+                // edge tile (reflect padding / short tail): the in-range part [k_lo, k_hi) still comes by
+                // TMA; the FFT warps fill the mirrored samples (at most one hop per side) themselves.
+                const int cnt = (nfr + 1) * H;
+                const int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);
+                if (lane == 0) {
+                    if (p.use_tma && k_hi > k_lo) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&samp_full[s], (uint32_t)(c_valid * (k_hi - k_lo) * sizeof(float)));
+                        for (int c = 0; c < c_valid; ++c)
+                            tma_load_1d(dst + c * (TT + 1) * H + k_lo, xg + (size_t)c * L + s0 + k_lo,
+                                        (uint32_t)((k_hi - k_lo) * sizeof(float)), &samp_full[s]);
+                    } else {
+                        mbar_arrive(&samp_full[s]);
+                    }
+                }
             }
         };
         if (SCM) acc_reset();
@@ -260,10 +272,14 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                     const float* xg = p.x + (size_t)grp * C * L;
                     float* dst = samp + s * SAMP;
                     const int cnt = (nfr + 1) * H;
+                    int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);   // [k_lo, k_hi) arrived by TMA
+                    if (!p.use_tma || k_hi <= k_lo) k_lo = k_hi = 0;
+                    const int n_fill = cnt - (k_hi - k_lo);
                     named_bar_sync(1, 32 * G::FFT_WARPS);     // every FFT warp is done with this stage
                     for (int c = 0; c < c_valid; ++c)
 #pragma unroll 4
-                        for (int k = w * 32 + lane; k < cnt; k += 32 * G::FFT_WARPS) {
+                        for (int q = w * 32 + lane; q < n_fill; q += 32 * G::FFT_WARPS) {
+                            const int k = q < k_lo ? q : q + (k_hi - k_lo);
                             int sidx = s0 + k;               // librosa center=True, pad_mode='reflect'
                             if (sidx < 0) sidx = -sidx;
                             if (sidx >= L) sidx = 2 * (L - 1) - sidx;
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&samp_empty[s]);   // all samples of this job are in registers
                 }
-                dft_reg<RA, false>(v);
+                if (!(p.dbg & 4)) dft_reg<RA, false>(v);
 #pragma unroll
                 for (int k1 = 0; k1 < RA; ++k1) {
                     const float2 val = (k1 == 0) ? v[0] : cmul(v[k1], TWREG ? twr[k1] : tw[k1 * 32 + lane]);
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
 #pragma unroll
             for (int l = 0; l < 32; ++l) u[l] = job[lane * 33 + l];
             __syncwarp();
-            dft_reg<32, false>(u);
+            if (!(p.dbg & 4)) dft_reg<32, false>(u);
             {
                 float2* row = job + (lane / RA) * ROWP + (lane % RA);
 #pragma unroll
@@ -364,9 +380,11 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                 for (int tl = 0; tl < TT; ++tl) {
                     float2 y[C];
                     unmix(stage, tl, f, y);
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) yc[c][tl * F] = y[c];
-                    if (SCM) acc_step(y, mcur[tl]);
+                        for (int c = 0; c < C; ++c) __stcs(&yc[c][tl * F], y[c]);
+                    }
+                    if (SCM && !(p.dbg & 2)) acc_step(y, mcur[tl]);
                 }
             } else {
 #pragma unroll
