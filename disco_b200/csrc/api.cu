@@ -202,7 +202,7 @@ static int make_cat(CatArgs* c, const void* Y, const void* Z, int n_utt, int K, 
                     const int* node_sel, int n_sel) {
     if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
     if (n_utt <= 0 || K < 1 || C < 1 || T < 1) return fail(DISCO_ERR_INVALID, "bad sizes");
-    if (C + K - 1 > 15) return fail(DISCO_ERR_UNSUPPORTED, "C + K - 1 must be <= 15");
+    if (C + K - 1 > 16) return fail(DISCO_ERR_UNSUPPORTED, "C + K - 1 must be <= 16");
     if (!Y || (K > 1 && !Z)) return fail(DISCO_ERR_INVALID, "null pointer");
     c->Y = (const float2*)Y;
     c->Z = (const float2*)Z;
@@ -293,7 +293,7 @@ int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rs
 int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
                     int rank, double mu, void* stream) {
     if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");
-    if (D < 1 || D > 15) return fail(DISCO_ERR_UNSUPPORTED, "D must be in 1..15");
+    if (D < 1 || D > 16) return fail(DISCO_ERR_UNSUPPORTED, "D must be in 1..16");
     if (n_mat < 0 || !Rss || !Rnn || !W) return fail(DISCO_ERR_INVALID, "bad arguments");
     SolveArgs a;
     memset(&a, 0, sizeof(a));

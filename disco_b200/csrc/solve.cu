@@ -12,11 +12,15 @@
 //   'r1-mwf' (:45-54)  w = l u conj(v_0) / (mu + l v^H u), (l, v) top eigenpair of Rss, u = Rnn^-1 v
 //   'mwf'    (:74-76)  w = (Rnn + Rss)^-1 Rss e_0
 //
-// One thread per matrix, float64 throughout (the SCMs arrive as complex64): the work is
-// O(n_mat * D^3) flops -- negligible next to the streaming kernels -- and double precision
-// keeps the result far inside the 1e-5 parity budget even for ill-conditioned bins.
-// Degenerate bins: a Cholesky pivot below 1e-13 * trace/D is floored there (diagonal
-// loading) so the output stays finite where LAPACK would return inf/NaN eigenvalues.
+// Float64 throughout (the SCMs arrive as complex64): the flop count is negligible next to the
+// streaming kernels and double precision keeps the result far inside the 1e-5 parity budget even
+// for ill-conditioned bins.  The work is latency-bound, so it is organised for short dependency
+// chains: a GROUP of G = 2/4/8/16 lanes (>= D) owns one matrix, 32/G matrices share a warp, the
+// matrices live in shared memory (no local-memory traffic), and every O(D) loop of the textbook
+// algorithms (column / row updates of a Jacobi rotation, the columns of a triangular solve, ...)
+// is spread over the group's lanes.  Groups synchronise with __syncwarp(group mask) only.
+// Degenerate bins: a Cholesky pivot below 1e-13 * trace/D is floored there (diagonal loading) so
+// the output stays finite where LAPACK would return inf/NaN eigenvalues.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,145 +42,201 @@ DISCO_DEV double norm2(cd a) { return a.x * a.x + a.y * a.y; }
 constexpr double kEps = 2.220446049250313e-16;  // sys.float_info.epsilon (internal_formulas.py:6)
 constexpr double kEta = 1e6;                    // internal_formulas.py:7
 
-// Row pitch of the per-thread matrices.  D = 16 is padded to 17: with a power-of-two pitch nvcc 12.9
-// miscompiles the 'gevd' branch (the same source built for the host is correct).
 template <int D>
-struct Ld {
-    static constexpr int v = (D == 16) ? 17 : D;
+struct SolveGeom {
+    static constexpr int G = D <= 2 ? 2 : (D <= 4 ? 4 : (D <= 8 ? 8 : 16));  // lanes per matrix
+    static constexpr int MPW = 32 / G;                                       // matrices per warp
+    static constexpr int P = (D % 2 == 0) ? D + 1 : D;   // odd row pitch (x16 B): conflict-free columns
+    static constexpr int MAT = D * P;                     // cd elements per matrix
+    static constexpr int WARPS = D <= 8 ? 4 : 2;
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int MPB = MPW * WARPS;               // matrices per block
+    static constexpr int NROT = (D + 1) / 2;              // rotations per Jacobi round
+    static constexpr size_t SMEM = (size_t)MPB * (3 * MAT * sizeof(cd) + NROT * 48);
 };
 
-// In-place lower Cholesky of the Hermitian matrix M (uses the lower triangle); returns L in M's
-// lower triangle with real positive diagonal.  Pivots are floored at `floor_`.
+// group-wide sum over the G lanes of a group (xor butterfly: fixed order, every lane gets the total)
+template <int G>
+DISCO_DEV double gsum(double v, unsigned gm) {
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(gm, v, off, G);
+    return v;
+}
+template <int G>
+DISCO_DEV cd gsum(cd v, unsigned gm) {
+    v.x = gsum<G>(v.x, gm);
+    v.y = gsum<G>(v.y, gm);
+    return v;
+}
+
+// In-place lower Cholesky of the Hermitian matrix M (lower triangle used) in shared memory.
+// Lane j computes pivot j, lanes i > j their entry of column j.
 template <int D>
-DISCO_DEV void cholesky(cd (&M)[D][Ld<D>::v], double floor_) {
-    constexpr int U = (D <= 4) ? D : 1;   // small matrices: fully unrolled, register resident
-#pragma unroll U
+DISCO_DEV void g_cholesky(cd* M, int l, unsigned gm, double floor_) {
+    constexpr int P = SolveGeom<D>::P, G = SolveGeom<D>::G;
     for (int j = 0; j < D; ++j) {
-        double d = M[j][j].x;
-        for (int k = 0; k < j; ++k) d -= norm2(M[j][k]);
-        d = fmax(d, floor_);
-        const double inv = rsqrt(d), l = d * inv;
-        M[j][j] = mk(l, 0.0);
-        for (int i = j + 1; i < D; ++i) {
-            cd s = M[i][j];
-            for (int k = 0; k < j; ++k) s = s - M[i][k] * conj(M[j][k]);
-            M[i][j] = inv * s;
+        double inv = 0.0;
+        if (l == j) {
+            double d = M[j * P + j].x;
+            for (int k = 0; k < j; ++k) d -= norm2(M[j * P + k]);
+            d = fmax(d, floor_);
+            inv = rsqrt(d);
+            M[j * P + j] = mk(d * inv, 0.0);
+        }
+        inv = __shfl_sync(gm, inv, j, G);
+        if (l > j && l < D) {
+            cd s = M[l * P + j];
+            for (int k = 0; k < j; ++k) s = s - M[l * P + k] * conj(M[j * P + k]);
+            M[l * P + j] = inv * s;
+        }
+        __syncwarp(gm);
+    }
+}
+
+// One Jacobi rotation (c, st) for the pivot pair (p, q); p < 0 marks "no rotation".
+struct Rot {
+    int p, q;
+    double c;
+    cd st;
+};
+
+// Parallel-order Jacobi of the Hermitian matrix A (destroyed) in shared memory; V <- eigenvectors
+// (columns).  Round-robin tournament: every sweep is N-1 rounds (N = D rounded up to even) of N/2
+// rotations on DISJOINT index pairs, so the N/2 expensive parameter computations of a round run
+// on N/2 different lanes at once (three float64 special functions each: rsqrt, sqrt+div, rsqrt),
+// then lane k applies all of them to row k of A and V (A <- A G, V <- V G), then to column k
+// (A <- G^H A).  The latency of a sweep is that of N-1 parameter chains instead of D(D-1)/2.
+template <int D>
+DISCO_DEV void g_jacobi(cd* A, cd* V, Rot* rot, int l, unsigned gm) {
+    constexpr int P = SolveGeom<D>::P, G = SolveGeom<D>::G;
+    constexpr int N = D + (D & 1), NP = N / 2;
+    const bool act = l < D;
+    double mine = 0.0;
+    if (act) {
+        for (int j = 0; j < D; ++j) {
+            V[l * P + j] = mk(j == l ? 1.0 : 0.0, 0.0);
+            mine += norm2(A[l * P + j]);
         }
     }
-}
-
-// One Jacobi rotation annihilating A[p][q] (and A[q][p]); A <- G^H A G, V <- V G.
-// Three expensive float64 operations per rotation (rsqrt, sqrt + div, rsqrt) instead of six.
-template <int D>
-DISCO_DEV void jacobi_rotate(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], int p, int q) {
-    const cd b = A[p][q];
-    const double n2 = norm2(b);
-    if (n2 < 1e-300) return;
-    const double inv_ab = rsqrt(n2), ab = n2 * inv_ab;
-    const cd ph = inv_ab * b;
-    const double d = 0.5 * (A[q][q].x - A[p][p].x);
-    const double t = copysign(ab, d) / (fabs(d) + sqrt(d * d + n2));   // tan of the rotation angle
-    const double c = rsqrt(1.0 + t * t), s = t * c;
-    const cd st = s * ph, stc = conj(st);
+    const double tot = gsum<G>(mine, gm);
+    __syncwarp(gm);
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double offm = 0.0;
+        if (act)
+            for (int j = l + 1; j < D; ++j) offm += norm2(A[l * P + j]);
+        const double off = gsum<G>(offm, gm);
+        if (off <= 1e-26 * tot) break;          // group-uniform
+        for (int r = 0; r < N - 1; ++r) {
+            if (l < NP) {                        // lane l owns pair l of this round (circle method)
+                int a0, b0;
+                if (l == 0) {
+                    a0 = N - 1;
+                    b0 = r;
+                } else {
+                    a0 = (r + l) % (N - 1);
+                    b0 = (r - l + (N - 1)) % (N - 1);
+                }
+                const int p = a0 < b0 ? a0 : b0, q = a0 < b0 ? b0 : a0;
+                Rot ro;
+                ro.p = -1;
+                ro.q = 0;
+                ro.c = 1.0;
+                ro.st = mk(0.0, 0.0);
+                if (q < D) {                     // q >= D: the dummy player of an odd D
+                    const cd b = A[p * P + q];
+                    const double n2 = norm2(b);
+                    if (n2 >= 1e-300) {
+                        const double inv_ab = rsqrt(n2), ab = n2 * inv_ab;
+                        const cd ph = inv_ab * b;
+                        const double d = 0.5 * (A[q * P + q].x - A[p * P + p].x);
+                        const double t = copysign(ab, d) / (fabs(d) + sqrt(d * d + n2));
+                        const double c = rsqrt(1.0 + t * t);
+                        ro.p = p;
+                        ro.q = q;
+                        ro.c = c;
+                        ro.st = (t * c) * ph;
+                    }
+                }
+                rot[l] = ro;
+            }
+            __syncwarp(gm);
+            if (act) {                          // A <- A G, V <- V G : row l, all pairs of the round
 #pragma unroll
-    for (int k = 0; k < D; ++k) {  // A <- A G
-        const cd akp = A[k][p], akq = A[k][q];
-        A[k][p] = c * akp - stc * akq;
-        A[k][q] = st * akp + c * akq;
-    }
+                for (int j = 0; j < NP; ++j) {
+                    const Rot ro = rot[j];
+                    if (ro.p < 0) continue;
+                    const cd st = ro.st, stc = conj(ro.st);
+                    const double c = ro.c;
+                    const cd akp = A[l * P + ro.p], akq = A[l * P + ro.q];
+                    A[l * P + ro.p] = c * akp - stc * akq;
+                    A[l * P + ro.q] = st * akp + c * akq;
+                    const cd vkp = V[l * P + ro.p], vkq = V[l * P + ro.q];
+                    V[l * P + ro.p] = c * vkp - stc * vkq;
+                    V[l * P + ro.q] = st * vkp + c * vkq;
+                }
+            }
+            __syncwarp(gm);
+            if (act) {                          // A <- G^H A : column l of the rows of every pair
 #pragma unroll
-    for (int k = 0; k < D; ++k) {  // A <- G^H A
-        const cd apk = A[p][k], aqk = A[q][k];
-        A[p][k] = c * apk - st * aqk;
-        A[q][k] = stc * apk + c * aqk;
-    }
-    A[p][q] = mk(0.0, 0.0);
-    A[q][p] = mk(0.0, 0.0);
-    A[p][p].y = 0.0;
-    A[q][q].y = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {  // V <- V G
-        const cd vkp = V[k][p], vkq = V[k][q];
-        V[k][p] = c * vkp - stc * vkq;
-        V[k][q] = st * vkp + c * vkq;
-    }
-}
-
-// Cyclic Jacobi for a Hermitian matrix A (destroyed); V receives the eigenvectors (columns),
-// lam the eigenvalues (unsorted).  Converged when the off-diagonal energy is below 1e-26 of the
-// total (the inputs carry float32 rounding, ~1e-14 relative energy).  For D <= 4 the (p, q) loops are
-// fully unrolled so that A and V live in registers; larger matrices index local memory.
-template <int D>
-DISCO_DEV void jacobi(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], double (&lam)[D]) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
-    double tot = 0.0;
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) tot += norm2(A[i][j]);
-#pragma unroll 1
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0;
-#pragma unroll
-        for (int p = 0; p < D; ++p)
-#pragma unroll
-            for (int q = p + 1; q < D; ++q) off += norm2(A[p][q]);
-        if (off <= 1e-26 * tot) break;
-        if constexpr (D <= 4) {
-#pragma unroll
-            for (int p = 0; p < D - 1; ++p)
-#pragma unroll
-                for (int q = p + 1; q < D; ++q) jacobi_rotate<D>(A, V, p, q);
-        } else {
-#pragma unroll 1
-            for (int p = 0; p < D - 1; ++p)
-#pragma unroll 1
-                for (int q = p + 1; q < D; ++q) jacobi_rotate<D>(A, V, p, q);
+                for (int j = 0; j < NP; ++j) {
+                    const Rot ro = rot[j];
+                    if (ro.p < 0) continue;
+                    const cd st = ro.st, stc = conj(ro.st);
+                    const double c = ro.c;
+                    const cd apk = A[ro.p * P + l], aqk = A[ro.q * P + l];
+                    cd np_ = c * apk - st * aqk, nq_ = stc * apk + c * aqk;
+                    if (l == ro.q) {
+                        np_ = mk(0.0, 0.0);     // the annihilated element and its mirror
+                        nq_.y = 0.0;
+                    }
+                    if (l == ro.p) {
+                        nq_ = mk(0.0, 0.0);
+                        np_.y = 0.0;
+                    }
+                    A[ro.p * P + l] = np_;
+                    A[ro.q * P + l] = nq_;
+                }
+            }
+            __syncwarp(gm);
         }
     }
-#pragma unroll
-    for (int i = 0; i < D; ++i) lam[i] = A[i][i].x;
+    __syncwarp(gm);
 }
 
+// Lane l builds row l of the Hermitian-symmetrised matrix from a complex64 [D][D] array.
 template <int D>
-DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][Ld<D>::v]) {
-    // Hermitian-symmetrise: the SCM kernels write exact conjugate mirrors, user input may not
-    for (int i = 0; i < D; ++i)
-        for (int j = 0; j <= i; ++j) {
-            const float2 a = R[i * D + j], b = R[j * D + i];
-            const cd v = mk(0.5 * ((double)a.x + (double)b.x), 0.5 * ((double)a.y - (double)b.y));
-            M[i][j] = v;
-            M[j][i] = conj(v);
+DISCO_DEV void g_load_herm(const float2* __restrict__ R, cd* M, int l) {
+    constexpr int P = SolveGeom<D>::P;
+    if (l < D)
+        for (int j = 0; j < D; ++j) {
+            const float2 a = R[l * D + j], b = R[j * D + l];
+            M[l * P + j] = mk(0.5 * ((double)a.x + (double)b.x), 0.5 * ((double)a.y - (double)b.y));
         }
 }
 
-// Rebuild one Hermitian matrix from the fused STFT+SCM kernel's partial sums: accumulator layout
+// Lane l builds row l from the fused STFT+SCM kernel's partial sums: accumulator layout
 // [D diagonals][D(D-1)/2 x (re, im) upper pairs, row-major], slots summed in order, scaled by 1/T
-// (same arithmetic as scm_finalize_kernel, so both routes give bit-identical matrices).
+// in float32 (the same arithmetic as scm_finalize_kernel: both routes give identical matrices).
 template <int D>
-DISCO_DEV void load_part(const float* __restrict__ q, int n_slot, size_t slot_stride, int F, float inv_T,
-                         cd (&M)[D][Ld<D>::v]) {
-    float acc[D * D];
-#pragma unroll
-    for (int a = 0; a < D * D; ++a) acc[a] = 0.f;
-    for (int sl = 0; sl < n_slot; ++sl) {
-#pragma unroll
-        for (int a = 0; a < D * D; ++a) acc[a] += __ldg(q + sl * slot_stride + (size_t)a * F);
-    }
-    int o = 0;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        M[i][i] = mk((double)(acc[i] * inv_T), 0.0);
-#pragma unroll
-        for (int j = i + 1; j < D; ++j) {
-            const cd v = mk((double)(acc[D + 2 * o] * inv_T), (double)(acc[D + 2 * o + 1] * inv_T));
-            M[i][j] = v;
-            M[j][i] = conj(v);
-            ++o;
+DISCO_DEV void g_load_part(const float* __restrict__ q, int n_slot, size_t slot_stride, int F, float inv_T, cd* M,
+                           int l) {
+    constexpr int P = SolveGeom<D>::P;
+    if (l >= D) return;
+    for (int j = 0; j < D; ++j) {
+        const int i0 = l < j ? l : j, j0 = l < j ? j : l;
+        float re = 0.f, im = 0.f;
+        if (i0 == j0) {
+            for (int sl = 0; sl < n_slot; ++sl) re += __ldg(q + sl * slot_stride + (size_t)i0 * F);
+        } else {
+            const int o = i0 * D - i0 * (i0 + 1) / 2 + (j0 - i0 - 1);
+            for (int sl = 0; sl < n_slot; ++sl) {
+                re += __ldg(q + sl * slot_stride + (size_t)(D + 2 * o) * F);
+                im += __ldg(q + sl * slot_stride + (size_t)(D + 2 * o + 1) * F);
+            }
         }
+        re *= inv_T;
+        im *= inv_T;
+        M[l * P + j] = mk((double)re, (double)(l <= j ? im : -im));
     }
 }
 
@@ -188,14 +248,24 @@ __device__ __forceinline__ int cta_of_tile_dev(long long i, long long total, int
     return b;
 }
 
-template <int D, int MINB, bool PART>
-__global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.n_mat) return;
-    constexpr int LD = Ld<D>::v;
-    cd S[D][LD], Nn[D][LD], V[D][LD];
-    cd w[D], t1[D];
-    for (int i = 0; i < D; ++i) t1[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);   // e_0 (internal_formulas.py:43)
+template <int D, bool PART>
+__global__ void __launch_bounds__(SolveGeom<D>::THREADS) mwf_solve_kernel(SolveArgs a) {
+    using SG = SolveGeom<D>;
+    constexpr int P = SG::P, G = SG::G;
+    extern __shared__ __align__(16) unsigned char solve_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp_in_warp = lane / G, l = lane % G;
+    const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
+    const int slot = warp * SG::MPW + grp_in_warp;
+    int idx = blockIdx.x * SG::MPB + slot;
+    const bool live = idx < a.n_mat;       // group-uniform; dead groups mirror the last matrix (no stores)
+    if (!live) idx = a.n_mat - 1;
+    Rot* rot = reinterpret_cast<Rot*>(solve_smem + (size_t)SG::MPB * 3 * SG::MAT * sizeof(cd)) + (size_t)slot * SG::NROT;
+    cd* S = reinterpret_cast<cd*>(solve_smem) + (size_t)slot * 3 * SG::MAT;   // Rss, then A
+    cd* Lm = S + SG::MAT;                                                      // Rnn, then its Cholesky factor
+    cd* V = Lm + SG::MAT;                                                      // eigenvectors
+    const bool act = l < D;
+
     if (PART) {
         const int g = idx / a.F, f = idx % a.F;
         const long long total = (long long)(a.n_mat / a.F) * a.tiles_per_grp;
@@ -203,148 +273,159 @@ __global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
         const int n_slot = cta_of_tile_dev((long long)(g + 1) * a.tiles_per_grp - 1, total, a.n_cta) - b_first + 1;
         const size_t slot_stride = (size_t)2 * D * D * a.F;
         const float* q = a.part + (size_t)g * a.slots_per_grp * slot_stride + f;
-        load_part<D>(q, n_slot, slot_stride, a.F, a.inv_T, S);
-        load_part<D>(q + (size_t)D * D * a.F, n_slot, slot_stride, a.F, a.inv_T, Nn);
-        if (a.Rss) {   // optionally also materialise the matrices (API output of the fused op)
+        g_load_part<D>(q, n_slot, slot_stride, a.F, a.inv_T, S, l);
+        g_load_part<D>(q + (size_t)D * D * a.F, n_slot, slot_stride, a.F, a.inv_T, Lm, l);
+        if (a.Rss && live && act) {   // optionally also materialise the matrices (API output of the fused op)
             float2* Rs = const_cast<float2*>(a.Rss) + (size_t)idx * D * D;
             float2* Rn = const_cast<float2*>(a.Rnn) + (size_t)idx * D * D;
-            for (int i = 0; i < D; ++i)
-                for (int j = 0; j < D; ++j) {
-                    Rs[i * D + j] = make_float2((float)S[i][j].x, (float)S[i][j].y);
-                    Rn[i * D + j] = make_float2((float)Nn[i][j].x, (float)Nn[i][j].y);
-                }
+            for (int j = 0; j < D; ++j) {
+                Rs[l * D + j] = make_float2((float)S[l * P + j].x, (float)S[l * P + j].y);
+                Rn[l * D + j] = make_float2((float)Lm[l * P + j].x, (float)Lm[l * P + j].y);
+            }
         }
     } else {
-        load_herm<D>(a.Rss + (size_t)idx * D * D, S);
-        load_herm<D>(a.Rnn + (size_t)idx * D * D, Nn);
+        g_load_herm<D>(a.Rss + (size_t)idx * D * D, S, l);
+        g_load_herm<D>(a.Rnn + (size_t)idx * D * D, Lm, l);
     }
-    double trn = 0.0, trs = 0.0;
-    for (int i = 0; i < D; ++i) trn += Nn[i][i].x, trs += S[i][i].x;
+    __syncwarp(gm);
+    // first row of Rnn (for conj((Rnn q)[0])) and the traces, before the matrices are overwritten
+    const cd n0 = act ? Lm[0 * P + l] : mk(0.0, 0.0);
+    const double trn = gsum<G>(act ? Lm[l * P + l].x : 0.0, gm);
+    const double trs = gsum<G>(act ? S[l * P + l].x : 0.0, gm);
+    cd w = mk(0.0, 0.0), t1 = mk((l == 0) ? 1.0 : 0.0, 0.0);   // t1 = e_0 (internal_formulas.py:43)
 
     if (a.type == 0) {  // ------------------------------------------------------------ gevd
-        cd Lm[D][LD];
-        for (int i = 0; i < D; ++i)
-            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
-        cholesky<D>(Lm, 1e-13 * trn / D + 1e-300);
-        // M = L^-1 S  (forward substitution, column by column), stored in S
-        for (int col = 0; col < D; ++col)
+        g_cholesky<D>(Lm, l, gm, 1e-13 * trn / D + 1e-300);
+        if (act) {      // M = L^-1 Rss : lane = column
             for (int i = 0; i < D; ++i) {
-                cd s = S[i][col];
-                for (int k = 0; k < i; ++k) s = s - Lm[i][k] * S[k][col];
-                S[i][col] = (1.0 / Lm[i][i].x) * s;
+                cd s = S[i * P + l];
+                for (int k = 0; k < i; ++k) s = s - Lm[i * P + k] * S[k * P + l];
+                S[i * P + l] = (1.0 / Lm[i * P + i].x) * s;
             }
-        // A = M L^-H  <=>  A^H = L^-1 M^H ; do it row-wise: for each row r of M solve x L^H = M[r]
-        for (int r = 0; r < D; ++r)
+        }
+        __syncwarp(gm);
+        if (act) {      // A = M L^-H : lane = row
             for (int j = 0; j < D; ++j) {
-                cd s = S[r][j];
-                for (int k = 0; k < j; ++k) s = s - S[r][k] * conj(Lm[j][k]);
-                S[r][j] = (1.0 / Lm[j][j].x) * s;
+                cd s = S[l * P + j];
+                for (int k = 0; k < j; ++k) s = s - S[l * P + k] * conj(Lm[j * P + k]);
+                S[l * P + j] = (1.0 / Lm[j * P + j].x) * s;
             }
-        for (int i = 0; i < D; ++i)   // enforce exact Hermitian symmetry
-            for (int j = 0; j < i; ++j) {
-                cd v = 0.5 * (S[i][j] + conj(S[j][i]));
-                S[i][j] = v;
-                S[j][i] = conj(v);
+        }
+        __syncwarp(gm);
+        if (act) {      // exact Hermitian symmetry: lane l owns the pairs (l, j < l)
+            for (int j = 0; j < l; ++j) {
+                const cd v = 0.5 * (S[l * P + j] + conj(S[j * P + l]));
+                S[l * P + j] = v;
+                S[j * P + l] = conj(v);
             }
-        double lam[D];
-        jacobi<D>(S, V, lam);
-        // Q = L^-H V : back substitution on each eigenvector
-        for (int col = 0; col < D; ++col)
+            S[l * P + l].y = 0.0;
+        }
+        __syncwarp(gm);
+        g_jacobi<D>(S, V, rot, l, gm);
+        if (act) {      // Q = L^-H V : lane = eigenvector (column), back substitution
             for (int i = D - 1; i >= 0; --i) {
-                cd s = V[i][col];
-                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * V[k][col];
-                V[i][col] = (1.0 / Lm[i][i].x) * s;
+                cd s = V[i * P + l];
+                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k * P + i]) * V[k * P + l];
+                V[i * P + l] = (1.0 / Lm[i * P + i].x) * s;
             }
-        for (int i = 0; i < D; ++i) w[i] = mk(0.0, 0.0);
+        }
+        __syncwarp(gm);
         const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
-        bool used[D];
-        for (int i = 0; i < D; ++i) used[i] = false;
-        for (int r = 0; r < rank; ++r) {  // r-th largest eigenvalue (selection, stable for ties)
+        unsigned used = 0;
+        for (int r = 0; r < rank; ++r) {   // r-th largest eigenvalue (every lane makes the same choice)
             int best = -1;
-            for (int i = 0; i < D; ++i)
-                if (!used[i] && (best < 0 || lam[i] > lam[best])) best = i;
-            used[best] = true;
-            const double l = fmin(fmax(lam[best], kEps), kEta);
-            cd c0 = mk(0.0, 0.0);  // (Rnn q)[0]
-            for (int j = 0; j < D; ++j) c0 = c0 + Nn[0][j] * V[j][best];
-            const cd cc = conj(c0);
-            const double g = l / (l + a.mu);
+            double lbest = 0.0;
             for (int i = 0; i < D; ++i) {
-                const cd qc = V[i][best] * cc;
-                w[i] = w[i] + g * qc;
-                if (r == 0) t1[i] = qc;
+                const double li = S[i * P + i].x;
+                if (!((used >> i) & 1u) && (best < 0 || li > lbest)) {
+                    best = i;
+                    lbest = li;
+                }
             }
+            used |= 1u << best;
+            const double lam = fmin(fmax(lbest, kEps), kEta);
+            const cd qi = act ? V[l * P + best] : mk(0.0, 0.0);
+            const cd c0 = gsum<G>(n0 * qi, gm);           // (Rnn q)[0] = sum_j Rnn[0][j] q[j]
+            const cd qc = qi * conj(c0);
+            w = w + (lam / (lam + a.mu)) * qc;
+            if (r == 0) t1 = qc;
         }
     } else if (a.type == 1) {  // -------------------------------------------------- r1-mwf
-        cd Lm[D][LD];
-        for (int i = 0; i < D; ++i)
-            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j];
-        double lam[D];
-        jacobi<D>(S, V, lam);
+        g_jacobi<D>(S, V, rot, l, gm);            // eigen-decomposition of Rss itself
         int best = 0;
         for (int i = 1; i < D; ++i)
-            if (lam[i] > lam[best]) best = i;
-        const double l = fabs(lam[best]);
-        cholesky<D>(Lm, 1e-13 * trn / D + 1e-300);
-        cd u[D];
-        for (int i = 0; i < D; ++i) {  // L y = v
-            cd s = V[i][best];
-            for (int k = 0; k < i; ++k) s = s - Lm[i][k] * u[k];
-            u[i] = (1.0 / Lm[i][i].x) * s;
+            if (S[i * P + i].x > S[best * P + best].x) best = i;
+        const double lmax = fabs(S[best * P + best].x);
+        g_cholesky<D>(Lm, l, gm, 1e-13 * trn / D + 1e-300);
+        __syncwarp(gm);
+        cd* u = S;                            // A is no longer needed: its first row is scratch for u = Rnn^-1 v
+        if (l == 0) {
+            for (int i = 0; i < D; ++i) {
+                cd s = V[i * P + best];
+                for (int k = 0; k < i; ++k) s = s - Lm[i * P + k] * u[k];
+                u[i] = (1.0 / Lm[i * P + i].x) * s;
+            }
+            for (int i = D - 1; i >= 0; --i) {
+                cd s = u[i];
+                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k * P + i]) * u[k];
+                u[i] = (1.0 / Lm[i * P + i].x) * s;
+            }
         }
-        for (int i = D - 1; i >= 0; --i) {  // L^H u = y
-            cd s = u[i];
-            for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * u[k];
-            u[i] = (1.0 / Lm[i][i].x) * s;
-        }
-        cd vhu = mk(0.0, 0.0);
-        for (int i = 0; i < D; ++i) vhu = vhu + conj(V[i][best]) * u[i];
-        // w = l u conj(v0) / (mu + l v^H u); the denominator is real for Hermitian Rnn
-        const cd den = mk(a.mu + l * vhu.x, l * vhu.y);
+        __syncwarp(gm);
+        const cd vl = act ? V[l * P + best] : mk(0.0, 0.0);
+        const cd ul = act ? u[l] : mk(0.0, 0.0);
+        const cd vhu = gsum<G>(conj(vl) * ul, gm);
+        const cd den = mk(a.mu + lmax * vhu.x, lmax * vhu.y);   // real for Hermitian Rnn up to rounding
         const double dn = 1.0 / norm2(den);
         const cd inv = mk(den.x * dn, -den.y * dn);
-        const cd sc = (l * conj(V[0][best])) * inv;
-        for (int i = 0; i < D; ++i) w[i] = u[i] * sc;
+        w = ul * ((lmax * conj(V[0 * P + best])) * inv);
     } else {  // ------------------------------------------------------------------------ mwf
-        cd Lm[D][LD];
-        for (int i = 0; i < D; ++i)
-            for (int j = 0; j < D; ++j) Lm[i][j] = Nn[i][j] + S[i][j];
-        cholesky<D>(Lm, 1e-13 * (trn + trs) / D + 1e-300);
-        for (int i = 0; i < D; ++i) {  // L y = Rss[:, 0]
-            cd s = S[i][0];
-            for (int k = 0; k < i; ++k) s = s - Lm[i][k] * w[k];
-            w[i] = (1.0 / Lm[i][i].x) * s;
+        if (act)
+            for (int j = 0; j < D; ++j) Lm[l * P + j] = Lm[l * P + j] + S[l * P + j];
+        __syncwarp(gm);
+        g_cholesky<D>(Lm, l, gm, 1e-13 * (trn + trs) / D + 1e-300);
+        cd* u = V;                            // scratch: first row of V
+        if (l == 0) {
+            for (int i = 0; i < D; ++i) {     // L y = Rss[:, 0]
+                cd s = S[i * P + 0];
+                for (int k = 0; k < i; ++k) s = s - Lm[i * P + k] * u[k];
+                u[i] = (1.0 / Lm[i * P + i].x) * s;
+            }
+            for (int i = D - 1; i >= 0; --i) {
+                cd s = u[i];
+                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k * P + i]) * u[k];
+                u[i] = (1.0 / Lm[i * P + i].x) * s;
+            }
         }
-        for (int i = D - 1; i >= 0; --i) {
-            cd s = w[i];
-            for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * w[k];
-            w[i] = (1.0 / Lm[i][i].x) * s;
-        }
+        __syncwarp(gm);
+        if (act) w = u[l];
     }
-    for (int i = 0; i < D; ++i) {
-        a.W[(size_t)idx * D + i] = make_float2((float)w[i].x, (float)w[i].y);
-        if (a.T1) a.T1[(size_t)idx * D + i] = make_float2((float)t1[i].x, (float)t1[i].y);
+    if (live && act) {
+        a.W[(size_t)idx * D + l] = make_float2((float)w.x, (float)w.y);
+        if (a.T1) a.T1[(size_t)idx * D + l] = make_float2((float)t1.x, (float)t1.y);
     }
 }
 
 template <int D>
 static cudaError_t launch_d(const SolveArgs& a, cudaStream_t st) {
-    if (a.part != nullptr) {
-        if (D > 4) return cudaErrorInvalidValue;
-        mwf_solve_kernel<(D > 4 ? 1 : D), 1, true><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
-    } else {
-        mwf_solve_kernel<D, 1, false><<<(a.n_mat + 63) / 64, 64, 0, st>>>(a);
+    using SG = SolveGeom<D>;
+    const int blocks = (a.n_mat + SG::MPB - 1) / SG::MPB;
+    auto kern = mwf_solve_kernel<D, false>;
+    if (SG::SMEM > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::SMEM);
+        if (e != cudaSuccess) return e;
     }
+    kern<<<blocks, SG::THREADS, SG::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
+cudaError_t launch_mwf_solve_small(const SolveArgs& a, cudaStream_t st);   // solve_small.cu (D <= 4, registers)
+
 cudaError_t launch_mwf_solve(const SolveArgs& a, cudaStream_t st) {
     if (a.n_mat <= 0) return cudaSuccess;
+    if (a.D <= 4) return launch_mwf_solve_small(a, st);
+    if (a.part != nullptr) return cudaErrorInvalidValue;
     switch (a.D) {
-        case 1: return launch_d<1>(a, st);
-        case 2: return launch_d<2>(a, st);
-        case 3: return launch_d<3>(a, st);
-        case 4: return launch_d<4>(a, st);
         case 5: return launch_d<5>(a, st);
         case 6: return launch_d<6>(a, st);
         case 7: return launch_d<7>(a, st);

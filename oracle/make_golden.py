@@ -26,6 +26,7 @@ TANGO_CASES = {
     # name: (seed, channels per node, L, vads, mask_for_z, outputs kept)
     "tango_k1c2_cfg1": (0, [2], 64000, ("irm1", "irm1"), "local", ("yf", "z_y")),
     "tango_k2c3_local": (1, [3, 3], 8192, ("irm1", "irm1"), "local", None),
+    "tango_k1c8_local": (11, [8], 24000, ("irm1", "irm1"), "local", ("yf", "z_y")),
     "tango_k3_ragged_local": (2, [2, 3, 2], 6000, ("irm1", "irm1"), "local", ("yf", "z_y", "zn", "sf")),
     "tango_k3c2_distant": (3, [2, 2, 2], 6000, ("irm1", "irm1"), "distant", ("yf", "z_y", "nf")),
     "tango_k2c4_irm2_iam1": (4, [4, 4], 24000, ("irm2", "iam1"), "local", ("yf", "z_y", "masks_z", "mask_w")),

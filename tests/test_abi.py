@@ -42,7 +42,7 @@ def test_argument_validation_without_gpu(lib):
     assert b"n_fft" in lib.disco_last_error()
     assert lib.disco_mwf_solve(None, None, None, None, 1, 4, 7, 1, 1.0, None) == -1
     assert b"Unknown filter reference" in lib.disco_last_error()
-    assert lib.disco_mwf_solve(None, None, None, None, 1, 16, 0, 1, 1.0, None) == -2
+    assert lib.disco_mwf_solve(None, None, None, None, 1, 17, 0, 1, 1.0, None) == -2
     assert lib.disco_tf_mask(None, None, None, 10, 5, 1, 0.0, None) == -1
     assert lib.disco_stft_scm_workspace(64, 4, 160000, 512) > 0
     with pytest.raises(_lib.DiscoError):

@@ -111,7 +111,7 @@ def test_mwf_solve_reference_kats(dev):
         ops.mwf_solve(Rxx[None], Rnn[None], 1.0, "nope", 1)
 
 
-@pytest.mark.parametrize("D", [1, 2, 4, 7, 9, 12, 15])
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 7, 9, 12, 15, 16])
 def test_mwf_solve_matches_f64(dev, D):
     from disco_b200 import ops
     from oracle import tango_f64

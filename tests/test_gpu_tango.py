@@ -160,3 +160,31 @@ def test_cuda_graph_plan_matches_eager(dev):
         plan.store("yf", host)
         torch.cuda.synchronize()
         assert torch.equal(host, ref["yf"].cpu())
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+@pytest.mark.parametrize("K,C", [(1, 8), (2, 2), (1, 3)])
+def test_tango_shapes_of_the_stft_sweep_config(dev, n_fft, K, C):
+    """BASELINE configs[3]: STFT-length sweep 256/512/1024 with 8 mics (and small-array variants):
+    each (utterance, node) within TOL of the float64 oracle, masks supplied on device."""
+    from disco_b200.synth import make_batch
+    from disco_b200.tango import tango_batched
+    from oracle import tango_f64
+    B, L = 2, 24000
+    y, _, _ = make_batch(B, K, C, L, seed0=300 + C)
+    T, F = 1 + L // (n_fft // 2), n_fft // 2 + 1
+    rng = np.random.default_rng(n_fft + C)
+    mz = rng.uniform(0.05, 0.95, size=(B, K, T, F)).astype(np.float32)
+    mw = rng.uniform(0.05, 0.95, size=(B, K, T, F)).astype(np.float32)
+    out = tango_batched(torch.from_numpy(y).to(dev), masks=(torch.from_numpy(mz).to(dev), torch.from_numpy(mw).to(dev)),
+                        n_fft=n_fft)
+    for b in range(B):
+        ref = tango_f64.offline_tango(y[b], masks=(mz[b].transpose(0, 2, 1), mw[b].transpose(0, 2, 1)),
+                                      n_fft=n_fft, n_hop=n_fft // 2)
+        # against EXACT arithmetic the budget grows with the channel count (conditioning of the 8-channel
+        # GEVD amplifies the float32 rounding of the spectra; the reference's own single-precision path is
+        # further away still -- parity with the reference at 8 mics is pinned by the tango_k1c8_local fixture)
+        tol = TOL if C <= 4 else 3e-5
+        for k in range(K):
+            assert rel_l2_mag(out["yf"][b, k].cpu().numpy(), ref["yf"][k]) < tol
+            assert rel_l2_mag(out["z_y"][b, k].cpu().numpy(), ref["z_y"][k]) < tol
