@@ -146,12 +146,17 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
         mask_z, mask_w = masks
         if mask_w is None:
             mask_w = mask_z
+    # mask_w may be a callable (Y, z_y, zn) -> [B, K, T, F]: a step-2 mask estimator that looks at the
+    # compressed signals of the other nodes (tango.py:387-394)
+    mask_w_fn = mask_w if callable(mask_w) else None
     # ---- step 1
     osn = (S, N) if "use_oracle_" in mask_for_z else None
     # single-node arrays: no exchange, so the step-1 filter-and-sum and the step-2 SCM share one pass over Y
-    fuse_mid = (K == 1 and mask_for_z == "local" and C <= 8)
+    fuse_mid = (K == 1 and mask_for_z == "local" and C <= 8 and mask_w_fn is None)
     st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn, apply_filter=not fuse_mid)
     Y, z_y, zn, W1 = st1["Y"], st1["z_y"], st1["zn"], st1["W1"]
+    if mask_w_fn is not None:
+        mask_w = mask_w_fn(Y, z_y, zn)
     R2 = None
     if fuse_mid:
         z_y, zn, Rss2, Rnn2 = ops.filter_sum_scm(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
@@ -215,7 +220,7 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
     masks_z, mask_w (float32; bool for 'ibmX' like the reference).
     Keyword-only extensions: n_fft, mu, filter_type, rank (module constants / literals in the
     reference) and masks=(mask_z[K], mask_w[K]) of (F, T) arrays for externally estimated masks.
-    DNN mask types ('crnn') through ``mods`` need disco_b200.dnn_mask.
+    DNN mask types ('crnn') run ``mods`` on the device through disco_b200.dnn_mask.
     """
     if mask_for_z is None:
         raise TypeError("argument of type 'NoneType' is not iterable")   # reference tango.py:343
@@ -225,9 +230,13 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
     chans = [len(y[k]) for k in range(K)]
     L = len(y[0][0])
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
-    if mods is not None and any(m is not None for m in mods) and masks is None:
-        raise NotImplementedError("DNN-estimated masks: pass masks=(mask_z, mask_w) or use disco_b200.dnn_mask")
     uniform = len(set(chans)) == 1
+    use_dnn = masks is None and any("rnn" in v for v in vads)
+    if use_dnn:
+        if not uniform:
+            raise NotImplementedError("DNN masks with ragged channel counts")
+        return _offline_tango_dnn(y, s, n, vads, mods, mask_for_z, z_sigs, n_fft, mu, filter_type, rank,
+                                  torch.device(device))
     dev = torch.device(device)
 
     def to_mask(mlist, nodes):
@@ -254,6 +263,50 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
             arr = arr.astype(np.float64)
         out.append([arr[k] for k in range(K)])
     return tuple(out)
+
+
+def _offline_tango_dnn(y, s, n, vads, mods, mask_for_z, z_sigs, n_fft, mu, filter_type, rank, dev):
+    """vads[i] == 'crnn' (or 'rnn'): masks predicted on the device by mods[i] (tango.py:209-215).
+    Step 1 feeds |Y_ref| alone; step 2 feeds |Y_0| plus the compressed signals of the other nodes chosen by
+    z_sigs (get_z_for_mask, tango.py:158-186); mods[1] is None with vads[1] == 'crnn' reuses the step-1 mask
+    (tango.py:388-389).  Window length / predicted frame are the reference's constants (tango.py:34-35)."""
+    from . import dnn_mask
+    K = len(y)
+    nodes = list(range(K))
+    yd, sd, nd = _to_dev(y, nodes, dev), _to_dev(s, nodes, dev), _to_dev(n, nodes, dev)
+    kw = dict(win_len=21, win_hop=1, frame_to_pred="mid", device=dev)
+    spec_ft = lambda a: a.transpose(-1, -2)                         # frame-major [T, F] -> (F, T) view
+
+    def oracle(kind, ch):
+        S, N = ops.stft(sd[:, :, ch].contiguous(), n_fft), ops.stft(nd[:, :, ch].contiguous(), n_fft)
+        return ops.tf_mask(S, N, kind)
+
+    if "rnn" in vads[0]:
+        Yref = ops.stft(yd[:, :, 0].contiguous(), n_fft)            # ref mic 0 (tango.py:338)
+        mask_z = torch.stack([dnn_mask.estimate_mask(mods[0], spec_ft(Yref[0, k]), None, **kw) for k in nodes])[None]
+    else:
+        mask_z = oracle(vads[0], 0)
+
+    def step2_mask(Y, z_y, zn):
+        if "rnn" not in vads[1]:
+            return oracle(vads[1], 0)
+        if mods[1] is None:
+            return mask_z
+        out = []
+        for k in nodes:
+            others = [j for j in nodes if j != k]
+            if z_sigs in ("zs_hat", "zn_hat"):
+                zin = z_y if z_sigs == "zs_hat" else zn
+                zl = [spec_ft(zin[0, j]) for j in others]
+            else:                                                     # interleaved zs_j, zn_j of the other nodes
+                zl = [spec_ft(t[0, j]) for j in others for t in (z_y, zn)]
+            out.append(dnn_mask.estimate_mask(mods[1], spec_ft(Y[0, k, 0]), zl, **kw))
+        return torch.stack(out)[None]
+
+    res = tango_batched(yd, sd, nd, masks=(mask_z, step2_mask), vads=vads, mask_for_z=mask_for_z, n_fft=n_fft,
+                        mu=mu, filter_type=filter_type, rank=rank, out_layout="FT")
+    res = {k: v[0].cpu().numpy() for k, v in res.items()}
+    return tuple([res[nm][k] for k in range(K)] for nm in OUTPUT_NAMES)
 
 
 def _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask):

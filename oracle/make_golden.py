@@ -146,6 +146,42 @@ def main():
     np.savez_compressed(os.path.join(OUT, "helpers_kat.npz"), **blob)
     print("helpers KATs written")
 
+    # ---- DNN-mask feeder: the reference's prepare_data + CRNN forward + reshape_mask on a tiny CRNN
+    import torch
+    torch.manual_seed(3)
+    rng = np.random.default_rng(5)
+    blob = {}
+    for n_ch in (1, 3):
+        model, _ = ref.build_crnn((n_ch, 21, 257), (4, 6, 6), (3, 3, 3), (1, 1, 1), [(1, 4)] * 3, (None,) * 3, [8],
+                                  "GRU", 257, conv_padding=[(0, 1)] * 3)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.data.uniform_(0.5, 1.5)
+                m.bias.data.normal_(0, 0.1)
+        model.eval()
+        T = 37
+        ysp = (rng.standard_normal((257, T)) + 1j * rng.standard_normal((257, T))).astype(np.complex64)
+        zsp = [(rng.standard_normal((257, T)) + 1j * rng.standard_normal((257, T))).astype(np.complex64)
+               for _ in range(n_ch - 1)]
+        lost = int(21 - model.get_loss_frames("last")[-1][-1])
+        tag = "c%d_" % n_ch
+        for k, v in model.state_dict().items():
+            blob[tag + "sd_" + k] = v.numpy()
+        blob[tag + "y"] = ysp
+        if zsp:
+            blob[tag + "z"] = np.array(zsp)
+        for ftp in ("mid", "last"):
+            xin = ref.prepare_data(ysp, True, z_data=zsp or None, win_len=21, win_hop=1, frame_to_pred=ftp,
+                                   frames_lost=lost)
+            with torch.no_grad():
+                blob[tag + "mask_" + ftp] = ref.reshape_mask(model(xin).numpy(), ftp)
+        blob[tag + "windows_mid_head"] = ref.prepare_data(ysp, True, z_data=zsp or None, win_len=21, win_hop=1,
+                                                          frame_to_pred="mid", frames_lost=lost)[:3].numpy()
+    np.savez_compressed(os.path.join(OUT, "crnn_kat.npz"), **blob)
+    print("CRNN KATs written")
+
 
 if __name__ == "__main__":
     main()
