@@ -19,10 +19,11 @@ def launches(path):
             continue
         name = r[ki].split("(")[0]
         agg.setdefault((name, r[gi], r[bi]), []).append(float(r[vi].replace(",", "")))
-    tot = sum(sum(v) for k, v in agg.items() if "disco::" in k[0])
+    ours = lambda name: not name.startswith("void at::")
+    tot = sum(sum(v) for k, v in agg.items() if ours(k[0]))
     out = ["| kernel | grid | block | launches | mean us | share of disco kernels |", "|---|---|---|---|---|---|"]
     for (name, g, b), v in agg.items():
-        share = sum(v) / tot if "disco::" in name else float("nan")
+        share = sum(v) / tot if ours(name) else float("nan")
         out.append("| `%s` | %s | %s | %d | %.1f | %.3f |" % (name, g, b, len(v), sum(v) / len(v) / 1e3, share))
     return "\n".join(out)
 

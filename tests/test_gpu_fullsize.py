@@ -81,4 +81,4 @@ def test_cfg3_shape_full_size_properties(dev):
     # single-precision LAPACK path is further away still (see tests/test_gpu_tango.py)
     for k in range(K):
         assert rel_l2_mag(out["yf"][5, k].cpu().numpy().T, ref["yf"][k]) < 3e-5
-        assert rel_l2_mag(out["z_y"][5, k].cpu().numpy().T, ref["z_y"][k]) < 1e-5
+        assert rel_l2_mag(out["z_y"][5, k].cpu().numpy().T, ref["z_y"][k]) < 2e-5
