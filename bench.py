@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="batch slices of the host-to-host pipeline")
     ap.add_argument("--chunks", type=int, default=1, help="batch chunks captured on parallel graph branches")
     args = ap.parse_args()
     B, K, C, L, n_fft, desc = WORKLOADS[args.workload]
@@ -293,10 +294,11 @@ def main():
     if not args.no_e2e:
         yf_host = torch.empty((B, K, T, F), dtype=torch.complex64).pin_memory()
 
-        def e2e_step():
-            plan.load(y_host, mz_host, mw_host)
-            plan.run()
-            plan.store("yf", yf_host)
+        from disco_b200.plan import TangoPipeline
+        pipe = TangoPipeline(B, K, C, L, n_fft=n_fft, chunks=args.e2e_chunks, device=dev)
+
+        def e2e_step():       # H2D of signals + masks, the whole path, D2H of yf -- overlapped across batch slices
+            pipe.process(y_host, mz_host, mw_host, yf_host)
         for _ in range(2):
             e2e_step()
         barrier()
@@ -311,7 +313,8 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": B * K * T * world * n_e2e / (float(t2.item()) / 1e3), "unit": "frames/s",
                "h2d_bytes_per_step": int(y_host.numel() * 4 + 2 * mz_host.numel() * 4),
-               "d2h_bytes_per_step": int(yf_host.numel() * 8), "steps": n_e2e}
+               "d2h_bytes_per_step": int(yf_host.numel() * 8), "steps": n_e2e,
+               "how": "TangoPipeline: %d batch slices, per-slice H2D -> graph replay -> D2H on its own stream (pinned host buffers)" % args.e2e_chunks}
     stop.set()
 
     if rank == 0:
@@ -322,13 +325,20 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg = stft_scm_bytes(C, L, n_fft) * B * K
+        traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of the kernel, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("workload") == args.workload and tj.get("batch") == B:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         if kern_ms is None:
             roof = {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "C > 4: stft and masked_scm run as two kernels; no fused-kernel roofline for this workload"}
         else:
           achieved = alg / (kern_ms / 1e3) / 1e9
           roof = {"bound": "hbm", "kernel": "stft_scm_kernel<%d,%d,true>" % (n_fft, C), "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / args.steps),
                 "timed": "CUDA events around the op in %d eager steps (the throughput region replays a CUDA graph)" % n_k}
         res = {"metric": "beamformed frames/sec (16kHz, 512-pt STFT)", "value": value, "unit": "frames/s", "n_gpus": world,
