@@ -127,9 +127,7 @@ DISCO_API int disco_filter_sum_scm(const void* W1, const void* Y, const float* m
 /* ---- per-bin MWF solve ---------------------------------------------------------------------------
  * Replaces intern_filter(Rxx, Rnn, mu, type, rank) (reference internal_formulas.py:31-81) for
  * n_mat matrices: Rss, Rnn [n_mat][D][D] complex64 -> W [n_mat][D], T1 [n_mat][D] complex64
- * (T1 may be NULL).  rank <= 0 means 'full'.  D <= 15 (the D = 16 instantiation of the 'gevd'
- * branch is miscompiled by nvcc 12.9 -- host build of the same source is correct -- and is disabled
- * until that is resolved).  Arithmetic in float64. */
+ * (T1 may be NULL).  rank <= 0 means 'full'.  D <= 16.  Arithmetic in float64. */
 DISCO_API int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
                     int rank, double mu, void* stream);
 
