@@ -74,3 +74,18 @@ def test_get_mask_ivad_matches_reference_golden():
         assert np.array_equal(m, g["masks_z_%d" % k])
     with pytest.raises(ValueError):
         get_mask(None, np.zeros((3, 3)), None, mask_type="nope")
+
+
+def test_get_z_signals_step1_twin():
+    """get_z_signals.offline_tango returns the step-1 outputs of the full Tango (same z_y, z_s, z_n, zn, masks)."""
+    from disco_b200.compat.get_z_signals import offline_tango as step1_only
+    from oracle.make_golden import NAMES, TANGO_CASES, case_inputs
+    seed, chans, length, vads, mfz, _ = TANGO_CASES["tango_k2c3_local"]
+    g = load_golden("tango_k2c3_local")
+    y, s, n = case_inputs(seed, chans, length, vads)
+    z_y, z_s, z_n, zn, mz = step1_only(y, s, n, "irm1", [None], "local")
+    for k in range(2):
+        for got, nm in ((z_y, "z_y"), (z_s, "z_s"), (z_n, "z_n"), (zn, "zn")):
+            ref = g["%s_%d" % (nm, k)]
+            assert np.linalg.norm(np.abs(got[k]) - np.abs(ref)) / np.linalg.norm(np.abs(ref)) < 1e-5
+        assert np.max(np.abs(mz[k] - g["masks_z_%d" % k])) < 5e-6
