@@ -112,6 +112,65 @@ __global__ void __launch_bounds__(256) filter_sum_kernel(FilterArgs a, int frame
     }
 }
 
+// Frame-major output (the pipeline's internal layout): pure streaming.  Thread (bin, way) handles frames
+// way, way + 8, ...; two register buffers of UF frames each are used alternately so UF * D loads per
+// thread are always in flight; FC > 0 makes the row stride a compile-time constant (F = 257).
+template <int D, int FC>
+__global__ void __launch_bounds__(256, (D <= 4 ? 2 : 1)) filter_sum_tf_kernel(FilterArgs a, int frames_per_slab) {
+    constexpr int UF = (D <= 4) ? 2 : 1;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int grp = blockIdx.y;
+    const int T = a.in.T, F = FC ? FC : a.in.F;
+    const int f = blockIdx.x * 32 + lane;
+    if (f >= F) return;
+    const int t_begin = blockIdx.z * frames_per_slab;
+    const int t_end = min(T, t_begin + frames_per_slab);
+    float2 w[D];
+    const float2* ch[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float2 v = a.W[((size_t)grp * F + f) * D + d];
+        w[d] = a.conj_w ? cconj(v) : v;
+        ch[d] = cat_channel_fs(a.in, grp, d) + f;
+    }
+    const float2* refch = cat_channel_fs(a.in, grp, a.ref) + f;
+    float2* out = a.out + (size_t)grp * T * F + f;
+    float2* res = a.resid ? a.resid + (size_t)grp * T * F + f : nullptr;
+    constexpr int TS = 8;                         // warps per block = time ways
+    auto load = [&](int t, float2 (&x)[UF][D], float2 (&r)[UF]) {
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            const int tt = t + u * TS;
+            const bool ok = tt < t_end;
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[u][d] = ok ? ch[d][tt * F] : make_float2(0.f, 0.f);
+            r[u] = (ok && res) ? refch[tt * F] : make_float2(0.f, 0.f);
+        }
+    };
+    auto emit = [&](int t, const float2 (&x)[UF][D], const float2 (&r)[UF]) {
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            const int tt = t + u * TS;
+            if (tt < t_end) {
+                float2 acc = cmul(w[0], x[u][0]);
+#pragma unroll
+                for (int d = 1; d < D; ++d) acc = cadd(acc, cmul(w[d], x[u][d]));
+                out[tt * F] = acc;
+                if (res) res[tt * F] = csub(r[u], acc);
+            }
+        }
+    };
+    float2 xa[UF][D], xb[UF][D], ra[UF], rb[UF];
+    int t = t_begin + wrp;
+    load(t, xa, ra);
+    for (; t < t_end; t += 2 * UF * TS) {
+        load(t + UF * TS, xb, rb);
+        emit(t, xa, ra);
+        load(t + 2 * UF * TS, xa, ra);
+        emit(t + UF * TS, xb, rb);
+    }
+}
+
 template <int D>
 static cudaError_t launch_d(const FilterArgs& a, cudaStream_t st) {
     const int fblocks = (a.in.F + 31) / 32;
@@ -122,7 +181,14 @@ static cudaError_t launch_d(const FilterArgs& a, cudaStream_t st) {
     int fps = ((a.in.T + slabs - 1) / slabs + 31) / 32 * 32;
     slabs = (a.in.T + fps - 1) / fps;
     dim3 grid(fblocks, a.in.n_grp, slabs);
-    filter_sum_kernel<D><<<grid, 256, 0, st>>>(a, fps);
+    if (!a.out_ft) {
+        if (D <= 4 && a.in.F == 257)
+            filter_sum_tf_kernel<D, (D <= 4 ? 257 : 0)><<<grid, 256, 0, st>>>(a, fps);
+        else
+            filter_sum_tf_kernel<D, 0><<<grid, 256, 0, st>>>(a, fps);
+    } else {
+        filter_sum_kernel<D><<<grid, 256, 0, st>>>(a, fps);
+    }
     return cudaGetLastError();
 }
 

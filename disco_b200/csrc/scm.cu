@@ -77,17 +77,20 @@ struct PairAcc {
     }
 };
 
-template <int D, int PART, bool ZF>
+// FC > 0: the number of bins is the compile-time constant FC (257 for the 512-point STFT), which turns
+// the row-stride multiplications of every address into immediates; FC == 0: runtime F.
+template <int D, int PART, bool ZF, int FC>
 DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int tw,
                               float2 (&ps)[ScmGeom<D>::NPP], float2 (&pn)[ScmGeom<D>::NPP]) {
     using G = ScmGeom<D>;
-    const int T = a.in.T, F = a.in.F;
+    const int T = a.in.T;
+    const int F = FC ? FC : a.in.F;
     const float2* ch[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) ch[d] = cat_channel(a.in, grp, d) + f;
     const float* mrow = a.mask ? (a.mask_ft ? a.mask + ((size_t)grp * F + f) * T : a.mask + (size_t)grp * T * F + f)
                                : nullptr;
-    const size_t mstride = a.mask_ft ? 1 : F;
+    const int mstride = a.mask_ft ? 1 : F;
     // fused step-1 filter (only the first pair-partition writes; K == 1 so D == C)
     constexpr bool zfuse = ZF && (PART == 0);
     float2 w1[D];
@@ -97,54 +100,82 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
     }
     float2* zrow = zfuse ? a.z_out + (size_t)grp * T * F + f : nullptr;
     float2* znrow = (zfuse && a.zn_out) ? a.zn_out + (size_t)grp * T * F + f : nullptr;
+    const int ref = a.ref;
     auto point = [&](const float2 (&y)[D], float m, int t) {
         const float wa = m * m, wb = mrow ? (1.f - m) * (1.f - m) : 0.f;
         PairAcc<D, PART, 0>::run(y, wa, wb, ps, pn);
         if (zfuse && active) {
-            float2 z = make_float2(0.f, 0.f);
+            float2 z = cmul(w1[0], y[0]);
 #pragma unroll
-            for (int d = 0; d < D; ++d) z = cadd(z, cmul(w1[d], y[d]));
-            zrow[(size_t)t * F] = z;
+            for (int d = 1; d < D; ++d) z = cadd(z, cmul(w1[d], y[d]));
+            zrow[t * F] = z;
             if (znrow) {
-                float2 r = make_float2(0.f, 0.f);
+                float2 r = y[0];
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    if (d == a.ref) r = y[d];
-                znrow[(size_t)t * F] = csub(r, z);
+                for (int d = 1; d < D; ++d)
+                    if (d == ref) r = y[d];
+                znrow[t * F] = csub(r, z);
             }
         }
     };
-    // Software pipeline over time: the loads of the NEXT pair of frames are issued before the
-    // current pair is consumed, so every thread keeps 2 D loads in flight while it computes.
-    auto load2 = [&](int t, float2 (&ya)[D], float2 (&yb)[D], float& ma, float& mb) {
-        const bool ha = active && t < T, hb = active && (t + G::TW) < T;
+    auto load1 = [&](int t, float2 (&y)[D], float& m) {
+        if (active && t < T) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            ya[d] = ha ? ch[d][(size_t)t * F] : make_float2(0.f, 0.f);
-            yb[d] = hb ? ch[d][(size_t)(t + G::TW) * F] : make_float2(0.f, 0.f);
+            for (int d = 0; d < D; ++d) y[d] = ch[d][t * F];
+            m = mrow ? mrow[t * mstride] : 1.f;
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = make_float2(0.f, 0.f);
+            m = 1.f;
         }
-        ma = (ha && mrow) ? mrow[(size_t)t * mstride] : 1.f;
-        mb = (hb && mrow) ? mrow[(size_t)(t + G::TW) * mstride] : 1.f;
     };
-    float2 na[D], nb[D];
-    float nma, nmb;
-    load2(tw, na, nb, nma, nmb);
-    for (int t = tw; t < T; t += 2 * G::TW) {
-        float2 y0[D], y1[D];
+    // Software pipeline over time with two register buffers used alternately (no copies): while
+    // buffer A is consumed the loads into buffer B are in flight, and vice versa.
+    constexpr int TS = G::TW;
+    float2 ya[D], yb[D];
+    float ma, mb;
+    int t = tw;
+    load1(t, ya, ma);
+    load1(t + TS, yb, mb);
+    for (; t + 3 * TS < T; t += 2 * TS) {       // both frames of this round and of the next exist
+        float2 yc[D], yd[D];
+        float mc, md;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            y0[d] = na[d];
-            y1[d] = nb[d];
+            yc[d] = ch[d][(t + 2 * TS) * F];
+            yd[d] = ch[d][(t + 3 * TS) * F];
         }
-        const float m0 = nma, m1 = nmb;
-        load2(t + 2 * G::TW, na, nb, nma, nmb);       // next iteration's loads (all-zero past the end)
-        point(y0, m0, t);
-        if (t + G::TW < T) point(y1, m1, t + G::TW);
+        mc = mrow ? mrow[(t + 2 * TS) * mstride] : 1.f;
+        md = mrow ? mrow[(t + 3 * TS) * mstride] : 1.f;
+        point(ya, ma, t);
+        point(yb, mb, t + TS);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            ya[d] = yc[d];
+            yb[d] = yd[d];
+        }
+        ma = mc;
+        mb = md;
+    }
+    for (; t < T; t += 2 * TS) {                // tail rounds (predicated loads)
+        float2 yc[D], yd[D];
+        float mc, md;
+        load1(t + 2 * TS, yc, mc);
+        load1(t + 3 * TS, yd, md);
+        point(ya, ma, t);
+        if (t + TS < T) point(yb, mb, t + TS);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            ya[d] = yc[d];
+            yb[d] = yd[d];
+        }
+        ma = mc;
+        mb = md;
     }
 }
 
-template <int D, bool ZF>
-__global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs a) {
+template <int D, bool ZF, int FC>
+__global__ void __launch_bounds__(ScmGeom<D>::THREADS, (D <= 4 ? 2 : 1)) masked_scm_kernel(ScmArgs a) {
     using G = ScmGeom<D>;
     extern __shared__ float2 red[];  // [NPART][NPP][2][32]
     const int lane = threadIdx.x & 31;
@@ -160,14 +191,14 @@ __global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs
     for (int q = 0; q < G::NPP; ++q) ps[q] = pn[q] = make_float2(0.f, 0.f);
 
     switch (part) {  // warp-uniform: keeps the (i, j) of every accumulator compile-time
-        case 0: scm_accumulate<D, 0, ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
-        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0), ZF>(a, grp, fc, active, tw, ps, pn); break;
+        case 0: scm_accumulate<D, 0, ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
+        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
     }
 
     // reduce the TW time-ways in fixed order: way w adds into way 0 through shared memory
@@ -219,11 +250,11 @@ __global__ void __launch_bounds__(ScmGeom<D>::THREADS) masked_scm_kernel(ScmArgs
     }
 }
 
-template <int D, bool ZF>
-static cudaError_t launch_dz(const ScmArgs& a, cudaStream_t st) {
+template <int D, bool ZF, int FC>
+static cudaError_t launch_dzf(const ScmArgs& a, cudaStream_t st) {
     using G = ScmGeom<D>;
     const size_t smem = (size_t)G::NPART * G::NPP * 2 * 32 * sizeof(float2);
-    auto kern = masked_scm_kernel<D, ZF>;
+    auto kern = masked_scm_kernel<D, ZF, FC>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -231,6 +262,13 @@ static cudaError_t launch_dz(const ScmArgs& a, cudaStream_t st) {
     dim3 grid((a.in.F + 31) / 32, a.in.n_grp);
     kern<<<grid, G::THREADS, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int D, bool ZF>
+static cudaError_t launch_dz(const ScmArgs& a, cudaStream_t st) {
+    // the 512-point STFT (F = 257) of small nodes is the hot configuration: compile-time row stride
+    if (D <= 4 && a.in.F == 257) return launch_dzf<D, ZF, (D <= 4 ? 257 : 0)>(a, st);
+    return launch_dzf<D, ZF, 0>(a, st);
 }
 
 template <int D>
