@@ -129,48 +129,65 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
             m = 1.f;
         }
     };
-    // Software pipeline over time with two register buffers used alternately (no copies): while
-    // buffer A is consumed the loads into buffer B are in flight, and vice versa.
+    // Software pipeline over time: the loads of the next round are in flight while this round's two
+    // frames are consumed.  Small D keeps two extra register buffers (loads issued straight into them);
+    // wide D reloads into the same pair after consuming it, which costs no extra registers.
     constexpr int TS = G::TW;
     float2 ya[D], yb[D];
     float ma, mb;
     int t = tw;
     load1(t, ya, ma);
     load1(t + TS, yb, mb);
-    for (; t + 3 * TS < T; t += 2 * TS) {       // both frames of this round and of the next exist
-        float2 yc[D], yd[D];
-        float mc, md;
+    if constexpr (D <= 4) {
+        for (; t + 3 * TS < T; t += 2 * TS) {   // both frames of this round and of the next exist
+            float2 yc[D], yd[D];
+            float mc, md;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            yc[d] = ch[d][(t + 2 * TS) * F];
-            yd[d] = ch[d][(t + 3 * TS) * F];
-        }
-        mc = mrow ? mrow[(t + 2 * TS) * mstride] : 1.f;
-        md = mrow ? mrow[(t + 3 * TS) * mstride] : 1.f;
-        point(ya, ma, t);
-        point(yb, mb, t + TS);
+            for (int d = 0; d < D; ++d) {
+                yc[d] = ch[d][(t + 2 * TS) * F];
+                yd[d] = ch[d][(t + 3 * TS) * F];
+            }
+            mc = mrow ? mrow[(t + 2 * TS) * mstride] : 1.f;
+            md = mrow ? mrow[(t + 3 * TS) * mstride] : 1.f;
+            point(ya, ma, t);
+            point(yb, mb, t + TS);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            ya[d] = yc[d];
-            yb[d] = yd[d];
+            for (int d = 0; d < D; ++d) {
+                ya[d] = yc[d];
+                yb[d] = yd[d];
+            }
+            ma = mc;
+            mb = md;
         }
-        ma = mc;
-        mb = md;
-    }
-    for (; t < T; t += 2 * TS) {                // tail rounds (predicated loads)
-        float2 yc[D], yd[D];
-        float mc, md;
-        load1(t + 2 * TS, yc, mc);
-        load1(t + 3 * TS, yd, md);
-        point(ya, ma, t);
-        if (t + TS < T) point(yb, mb, t + TS);
+        for (; t < T; t += 2 * TS) {            // tail rounds (predicated loads)
+            float2 yc[D], yd[D];
+            float mc, md;
+            load1(t + 2 * TS, yc, mc);
+            load1(t + 3 * TS, yd, md);
+            point(ya, ma, t);
+            if (t + TS < T) point(yb, mb, t + TS);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            ya[d] = yc[d];
-            yb[d] = yd[d];
+            for (int d = 0; d < D; ++d) {
+                ya[d] = yc[d];
+                yb[d] = yd[d];
+            }
+            ma = mc;
+            mb = md;
         }
-        ma = mc;
-        mb = md;
+    } else {
+        for (; t < T; t += 2 * TS) {
+            float2 y0[D], y1[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                y0[d] = ya[d];
+                y1[d] = yb[d];
+            }
+            const float m0 = ma, m1 = mb;
+            load1(t + 2 * TS, ya, ma);
+            load1(t + 3 * TS, yb, mb);
+            point(y0, m0, t);
+            if (t + TS < T) point(y1, m1, t + TS);
+        }
     }
 }
 
