@@ -203,6 +203,78 @@ DISCO_DEV void g_jacobi(cd* A, cd* V, Rot* rot, int l, unsigned gm) {
     __syncwarp(gm);
 }
 
+// Principal eigenpair of the Hermitian positive semi-definite matrix A (shared memory, preserved) by
+// repeated squaring: B_0 = A / tr A, B_{k+1} = B_k^2 / tr(B_k^2) converges to v v^H with the eigenvalue
+// ratio raised to the power 2^k, i.e. 10 squarings resolve a 3 % gap to 1e-14 and 24 squarings a
+// 1e-5 gap -- a dozen small matrix products instead of ~50 Jacobi rounds with their float64 special
+// functions.  Rank-1 is detected by ||B||_F^2 = 1 (tr B = 1).  Lane l owns row l.  Returns this
+// lane's component of the unit eigenvector (in *v_out) and the eigenvalue v^H A v.
+// Used for the rank-1 GEVD-MWF (the only form Tango calls, tango.py:367, :443); rank > 1 keeps Jacobi.
+template <int D>
+DISCO_DEV double g_top_eigpair(const cd* A, cd* B, int l, unsigned gm, cd* v_out) {
+    constexpr int P = SolveGeom<D>::P, G = SolveGeom<D>::G;
+    const bool act = l < D;
+    const double tr = gsum<G>(act ? A[l * P + l].x : 0.0, gm);
+    if (!(tr > 1e-300)) {                       // zero matrix: any unit vector, eigenvalue 0
+        *v_out = mk(l == 0 ? 1.0 : 0.0, 0.0);
+        return 0.0;
+    }
+    if (act) {
+        const double it = 1.0 / tr;
+        for (int j = 0; j < D; ++j) B[l * P + j] = it * A[l * P + j];
+    }
+    __syncwarp(gm);
+    for (int iter = 0; iter < 40; ++iter) {
+        cd c[D];
+        double fro = 0.0, dg = 0.0;
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) c[j] = mk(0.0, 0.0);
+            for (int k = 0; k < D; ++k) {
+                const cd blk = B[l * P + k];
+#pragma unroll
+                for (int j = 0; j < D; ++j) c[j] = c[j] + blk * B[k * P + j];
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                fro += norm2(c[j]);
+                if (j == l) dg = c[j].x;
+            }
+        }
+        const double trc = gsum<G>(dg, gm);      // tr(B^2) = ||B||_F^2 of the previous iterate (<= 1)
+        const double fr2 = gsum<G>(fro, gm);     // ||B^2||_F^2
+        __syncwarp(gm);                          // everyone has finished reading B
+        if (act) {
+            const double it = 1.0 / trc;
+#pragma unroll
+            for (int j = 0; j < D; ++j) B[l * P + j] = it * c[j];
+            B[l * P + l].y = 0.0;
+        }
+        __syncwarp(gm);
+        if (1.0 - fr2 / (trc * trc) <= 1e-14) break;   // new iterate is rank one (group-uniform)
+    }
+    // B ~ v v^H: take the column with the largest diagonal, normalise
+    int jm = 0;
+    double dmax = B[0].x;
+    for (int j = 1; j < D; ++j)
+        if (B[j * P + j].x > dmax) {
+            dmax = B[j * P + j].x;
+            jm = j;
+        }
+    cd v = act ? B[l * P + jm] : mk(0.0, 0.0);
+    const double nv = gsum<G>(norm2(v), gm);
+    v = rsqrt(nv) * v;
+    __syncwarp(gm);
+    if (act) B[l] = v;                           // row 0 of B as a scratch vector (B is dead now)
+    __syncwarp(gm);
+    cd av = mk(0.0, 0.0);
+    if (act)
+        for (int j = 0; j < D; ++j) av = av + A[l * P + j] * B[j];
+    const cd lam = gsum<G>(conj(v) * av, gm);
+    *v_out = v;
+    return lam.x;
+}
+
 // Lane l builds row l of the Hermitian-symmetrised matrix from a complex64 [D][D] array.
 template <int D>
 DISCO_DEV void g_load_herm(const float2* __restrict__ R, cd* M, int l) {
@@ -321,34 +393,58 @@ __global__ void __launch_bounds__(SolveGeom<D>::THREADS) mwf_solve_kernel(SolveA
             S[l * P + l].y = 0.0;
         }
         __syncwarp(gm);
-        g_jacobi<D>(S, V, rot, l, gm);
-        if (act) {      // Q = L^-H V : lane = eigenvector (column), back substitution
+        if (a.rank == 1) {
+            // rank-1 GEVD-MWF: only the principal pair is needed
+            cd v;
+            const double lam1 = g_top_eigpair<D>(S, V, l, gm, &v);
+            // q = L^-H v : column-oriented back substitution, one broadcast per step
+            cd q = v;
             for (int i = D - 1; i >= 0; --i) {
-                cd s = V[i * P + l];
-                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k * P + i]) * V[k * P + l];
-                V[i * P + l] = (1.0 / Lm[i * P + i].x) * s;
+                cd qi = mk(0.0, 0.0);
+                if (l == i) {
+                    q = (1.0 / Lm[i * P + i].x) * q;
+                    qi = q;
+                }
+                qi.x = __shfl_sync(gm, qi.x, i, G);
+                qi.y = __shfl_sync(gm, qi.y, i, G);
+                if (l < i) q = q - conj(Lm[i * P + l]) * qi;
             }
-        }
-        __syncwarp(gm);
-        const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
-        unsigned used = 0;
-        for (int r = 0; r < rank; ++r) {   // r-th largest eigenvalue (every lane makes the same choice)
-            int best = -1;
-            double lbest = 0.0;
-            for (int i = 0; i < D; ++i) {
-                const double li = S[i * P + i].x;
-                if (!((used >> i) & 1u) && (best < 0 || li > lbest)) {
-                    best = i;
-                    lbest = li;
+            if (!act) q = mk(0.0, 0.0);
+            const double lam = fmin(fmax(lam1, kEps), kEta);
+            const cd c0 = gsum<G>(n0 * q, gm);            // (Rnn q)[0] = sum_j Rnn[0][j] q[j]
+            const cd qc = q * conj(c0);
+            w = (lam / (lam + a.mu)) * qc;
+            t1 = qc;
+        } else {
+        g_jacobi<D>(S, V, rot, l, gm);
+            if (act) {      // Q = L^-H V : lane = eigenvector (column), back substitution
+                for (int i = D - 1; i >= 0; --i) {
+                    cd s = V[i * P + l];
+                    for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k * P + i]) * V[k * P + l];
+                    V[i * P + l] = (1.0 / Lm[i * P + i].x) * s;
                 }
             }
-            used |= 1u << best;
-            const double lam = fmin(fmax(lbest, kEps), kEta);
-            const cd qi = act ? V[l * P + best] : mk(0.0, 0.0);
-            const cd c0 = gsum<G>(n0 * qi, gm);           // (Rnn q)[0] = sum_j Rnn[0][j] q[j]
-            const cd qc = qi * conj(c0);
-            w = w + (lam / (lam + a.mu)) * qc;
-            if (r == 0) t1 = qc;
+            __syncwarp(gm);
+            const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
+            unsigned used = 0;
+            for (int r = 0; r < rank; ++r) {   // r-th largest eigenvalue (every lane makes the same choice)
+                int best = -1;
+                double lbest = 0.0;
+                for (int i = 0; i < D; ++i) {
+                    const double li = S[i * P + i].x;
+                    if (!((used >> i) & 1u) && (best < 0 || li > lbest)) {
+                        best = i;
+                        lbest = li;
+                    }
+                }
+                used |= 1u << best;
+                const double lam = fmin(fmax(lbest, kEps), kEta);
+                const cd qi = act ? V[l * P + best] : mk(0.0, 0.0);
+                const cd c0 = gsum<G>(n0 * qi, gm);           // (Rnn q)[0] = sum_j Rnn[0][j] q[j]
+                const cd qc = qi * conj(c0);
+                w = w + (lam / (lam + a.mu)) * qc;
+                if (r == 0) t1 = qc;
+            }
         }
     } else if (a.type == 1) {  // -------------------------------------------------- r1-mwf
         g_jacobi<D>(S, V, rot, l, gm);            // eigen-decomposition of Rss itself
