@@ -127,6 +127,86 @@ DISCO_DEV void jacobi(cd (&A)[D][Ld<D>::v], cd (&V)[D][Ld<D>::v], double (&lam)[
     for (int i = 0; i < D; ++i) lam[i] = A[i][i].x;
 }
 
+// Principal eigenpair of the Hermitian PSD matrix A by repeated squaring (see solve.cu g_top_eigpair):
+// B <- B^2 / tr(B^2) until ||B||_F^2 = 1 (rank one).  Fully unrolled: B and its square live in
+// registers.  v receives the unit eigenvector, the return value is v^H A v.
+template <int D>
+DISCO_DEV double top_eigpair(const cd (&A)[D][Ld<D>::v], cd (&v)[D]) {
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) tr += A[i][i].x;
+    if (!(tr > 1e-300)) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);
+        return 0.0;
+    }
+    cd B[D][D];
+    {
+        const double it = 1.0 / tr;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) B[i][j] = it * A[i][j];
+    }
+#pragma unroll 1
+    for (int iter = 0; iter < 40; ++iter) {
+        cd C[D][D];
+        double trc = 0.0, fr2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {           // Hermitian: upper triangle only
+                cd c = B[i][0] * B[0][j];
+#pragma unroll
+                for (int k = 1; k < D; ++k) c = c + B[i][k] * B[k][j];
+                C[i][j] = c;
+                if (i == j) {
+                    trc += c.x;
+                    fr2 += c.x * c.x;
+                } else {
+                    fr2 += 2.0 * norm2(c);
+                }
+            }
+        const double it = 1.0 / trc;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            B[i][i] = mk(it * C[i][i].x, 0.0);
+#pragma unroll
+            for (int j = i + 1; j < D; ++j) {
+                B[i][j] = it * C[i][j];
+                B[j][i] = conj(B[i][j]);
+            }
+        }
+        if (1.0 - fr2 * it * it <= 1e-14) break;
+    }
+    int jm = 0;
+#pragma unroll
+    for (int j = 1; j < D; ++j)
+        if (B[j][j].x > B[jm][jm].x) jm = j;
+    double nv = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        cd c = B[i][0];
+#pragma unroll
+        for (int j = 1; j < D; ++j)
+            if (j == jm) c = B[i][j];
+        v[i] = c;
+        nv += norm2(c);
+    }
+    const double inv = rsqrt(nv);
+    double lam = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = inv * v[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        cd av = A[i][0] * v[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) av = av + A[i][j] * v[j];
+        lam += (conj(v[i]) * av).x;
+    }
+    return lam;
+}
+
 template <int D>
 DISCO_DEV void load_herm(const float2* __restrict__ R, cd (&M)[D][Ld<D>::v]) {
     // Hermitian-symmetrise: the SCM kernels write exact conjugate mirrors, user input may not
@@ -232,33 +312,53 @@ __global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
                 S[i][j] = v;
                 S[j][i] = conj(v);
             }
-        double lam[D];
-        jacobi<D>(S, V, lam);
-        // Q = L^-H V : back substitution on each eigenvector
-        for (int col = 0; col < D; ++col)
-            for (int i = D - 1; i >= 0; --i) {
-                cd s = V[i][col];
-                for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * V[k][col];
-                V[i][col] = (1.0 / Lm[i][i].x) * s;
+        if (a.rank == 1) {   // rank-1 GEVD-MWF (tango.py:367, :443): principal pair only, by repeated squaring
+            cd q[D];
+            const double lam1 = top_eigpair<D>(S, q);
+            for (int i = D - 1; i >= 0; --i) {       // q = L^-H v
+                cd sacc = q[i];
+                for (int k = i + 1; k < D; ++k) sacc = sacc - conj(Lm[k][i]) * q[k];
+                q[i] = (1.0 / Lm[i][i].x) * sacc;
             }
-        for (int i = 0; i < D; ++i) w[i] = mk(0.0, 0.0);
-        const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
-        bool used[D];
-        for (int i = 0; i < D; ++i) used[i] = false;
-        for (int r = 0; r < rank; ++r) {  // r-th largest eigenvalue (selection, stable for ties)
-            int best = -1;
-            for (int i = 0; i < D; ++i)
-                if (!used[i] && (best < 0 || lam[i] > lam[best])) best = i;
-            used[best] = true;
-            const double l = fmin(fmax(lam[best], kEps), kEta);
-            cd c0 = mk(0.0, 0.0);  // (Rnn q)[0]
-            for (int j = 0; j < D; ++j) c0 = c0 + Nn[0][j] * V[j][best];
+            const double l = fmin(fmax(lam1, kEps), kEta);
+            cd c0 = mk(0.0, 0.0);                    // (Rnn q)[0]
+            for (int j = 0; j < D; ++j) c0 = c0 + Nn[0][j] * q[j];
             const cd cc = conj(c0);
             const double g = l / (l + a.mu);
             for (int i = 0; i < D; ++i) {
-                const cd qc = V[i][best] * cc;
-                w[i] = w[i] + g * qc;
-                if (r == 0) t1[i] = qc;
+                const cd qc = q[i] * cc;
+                w[i] = g * qc;
+                t1[i] = qc;
+            }
+        } else {
+        double lam[D];
+            jacobi<D>(S, V, lam);
+            // Q = L^-H V : back substitution on each eigenvector
+            for (int col = 0; col < D; ++col)
+                for (int i = D - 1; i >= 0; --i) {
+                    cd s = V[i][col];
+                    for (int k = i + 1; k < D; ++k) s = s - conj(Lm[k][i]) * V[k][col];
+                    V[i][col] = (1.0 / Lm[i][i].x) * s;
+                }
+            for (int i = 0; i < D; ++i) w[i] = mk(0.0, 0.0);
+            const int rank = (a.rank <= 0 || a.rank > D) ? D : a.rank;
+            bool used[D];
+            for (int i = 0; i < D; ++i) used[i] = false;
+            for (int r = 0; r < rank; ++r) {  // r-th largest eigenvalue (selection, stable for ties)
+                int best = -1;
+                for (int i = 0; i < D; ++i)
+                    if (!used[i] && (best < 0 || lam[i] > lam[best])) best = i;
+                used[best] = true;
+                const double l = fmin(fmax(lam[best], kEps), kEta);
+                cd c0 = mk(0.0, 0.0);  // (Rnn q)[0]
+                for (int j = 0; j < D; ++j) c0 = c0 + Nn[0][j] * V[j][best];
+                const cd cc = conj(c0);
+                const double g = l / (l + a.mu);
+                for (int i = 0; i < D; ++i) {
+                    const cd qc = V[i][best] * cc;
+                    w[i] = w[i] + g * qc;
+                    if (r == 0) t1[i] = qc;
+                }
             }
         }
     } else if (a.type == 1) {  // -------------------------------------------------- r1-mwf
