@@ -225,7 +225,8 @@ def main():
     ops.init(n_fft)
     from disco_b200.plan import TangoGraph
     chunks = max(1, min(args.chunks, B))
-    kernels_per_chunk = 5 if K == 1 else 6   # stft_scm, mwf_solve, [filter_sum,] masked_scm, mwf_solve, filter_sum
+    # stft_scm, mwf_solve, fused middle pass (or filter_sum + masked_scm), mwf_solve, filter_sum
+    kernels_per_chunk = 5 if (K == 1 or ops.tango_mid_supported(C, K)) else 6
     launches_per_step = kernels_per_chunk * chunks
     plan = TangoGraph(B, K, C, L, n_fft=n_fft, chunks=chunks, device=dev)   # CUDA graph of the whole step
     plan.load(y, mz, mw)

@@ -29,6 +29,9 @@ SIGNATURES = {
                                  c_int, c_int_p, c_int, c_void_p]),
     "disco_filter_sum_scm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p]),
+    "disco_tango_mid_supported": (c_int, [c_int, c_int]),
+    "disco_tango_mid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p]),
     "disco_mwf_solve_workspace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_int, c_int, c_double, c_void_p]),
     "disco_mwf_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,

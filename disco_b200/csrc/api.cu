@@ -262,6 +262,33 @@ int disco_filter_sum_scm(const void* W1, const void* Y, const float* mask, int m
     return 0;
 }
 
+int disco_tango_mid_supported(int C, int K) { return tango_mid_supported(C, K) ? 1 : 0; }
+
+int disco_tango_mid(const void* W1, const void* Y, const float* mask_w, void* Z, void* ZN, int ref, void* Rss,
+                    void* Rnn, int n_utt, int K, int C, int T, int n_fft, void* stream) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (!W1 || !Y || !mask_w || !Z || !Rss || !Rnn || n_utt < 1 || T < 1)
+        return fail(DISCO_ERR_INVALID, "bad arguments");
+    if (!tango_mid_supported(C, K)) return fail(DISCO_ERR_UNSUPPORTED, "no fused middle pass for this (C, K)");
+    if (ref < 0 || ref >= C) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    MidArgs a;
+    a.Y = (const float2*)Y;
+    a.W1 = (const float2*)W1;
+    a.mask = mask_w;
+    a.Z = (float2*)Z;
+    a.ZN = (float2*)ZN;
+    a.Rss = (float2*)Rss;
+    a.Rnn = (float2*)Rnn;
+    a.B = n_utt;
+    a.K = K;
+    a.C = C;
+    a.T = T;
+    a.F = n_fft / 2 + 1;
+    a.ref = ref;
+    CU(launch_tango_mid(a, (cudaStream_t)stream), "tango_mid launch");
+    return 0;
+}
+
 int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp, int C,
                               int length, int n_fft, int filter_type, int rank, double mu, void* stream) {
     if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");

@@ -82,6 +82,20 @@ struct FilterArgs {
 };
 cudaError_t launch_filter_sum(const FilterArgs& a, cudaStream_t st);
 
+// Fused multi-node middle pass (mid_multi.cu): z, zn of every node + step-2 SCMs of every node.
+struct MidArgs {
+    const float2* Y;     // [B*K][C][T][F]
+    const float2* W1;    // [B*K][F][C]  step-1 filters
+    const float* mask;   // [B*K][T][F]  step-2 masks (frame-major only)
+    float2* Z;           // [B][K][T][F] out
+    float2* ZN;          // [B][K][T][F] out (may be null)
+    float2* Rss;         // [B*K][F][D][D] out, D = C + K - 1, reference channel order
+    float2* Rnn;
+    int B, K, C, T, F, ref;
+};
+cudaError_t launch_tango_mid(const MidArgs& a, cudaStream_t st);
+bool tango_mid_supported(int C, int K);
+
 struct IstftArgs {
     const float2* Y;     // [n_sig][T][F] frame-major complex64
     float* x;            // [n_sig][L]

@@ -189,6 +189,29 @@ def filter_sum_scm(W1, Y, mask, ref=0, n_fft=512, mask_layout="TF"):
     return z, zn, Rss, Rnn
 
 
+def tango_mid_supported(C, K):
+    return bool(_lib.load().disco_tango_mid_supported(int(C), int(K)))
+
+
+def tango_mid(W1, Y, mask_w, ref=0, n_fft=512):
+    """Multi-node arrays: z, zn of every node AND the step-2 SCMs of every node in one pass over Y.
+    W1 [B, K, F, C], Y [B, K, C, T, F], mask_w [B, K, T, F] -> z, zn [B, K, T, F], Rss, Rnn [B, K, F, D, D]."""
+    _need(W1, torch.complex64, "W1")
+    _need(Y, torch.complex64, "Y")
+    _need(mask_w, torch.float32, "mask_w")
+    B, K, C, T, F = Y.shape
+    D = C + K - 1
+    if tuple(W1.shape) != (B, K, F, C) or tuple(mask_w.shape) != (B, K, T, F):
+        raise ValueError("shape mismatch")
+    z = torch.empty((B, K, T, F), dtype=torch.complex64, device=Y.device)
+    zn = torch.empty_like(z)
+    Rss = torch.empty((B, K, F, D, D), dtype=torch.complex64, device=Y.device)
+    Rnn = torch.empty_like(Rss)
+    _lib.check(_lib.load().disco_tango_mid(_ptr(W1), _ptr(Y), _ptr(mask_w), _ptr(z), _ptr(zn), int(ref), _ptr(Rss),
+                                           _ptr(Rnn), B, K, C, T, n_fft, _stream()))
+    return z, zn, Rss, Rnn
+
+
 def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
     """Batched intern_filter (reference internal_formulas.py:31-81).  Rss, Rnn [..., D, D] complex64
     -> W [..., D], t1 [..., D] complex64.  rank 'full'/'Full'/None -> all eigenpairs."""

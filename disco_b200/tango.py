@@ -153,13 +153,20 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     osn = (S, N) if "use_oracle_" in mask_for_z else None
     # single-node arrays: no exchange, so the step-1 filter-and-sum and the step-2 SCM share one pass over Y
     fuse_mid = (K == 1 and mask_for_z == "local" and C <= 8 and mask_w_fn is None)
-    st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn, apply_filter=not fuse_mid)
+    # multi-node arrays: z of every node + the step-2 SCMs of every node in one pass over Y
+    fuse_multi = (K > 1 and mask_for_z == "local" and mask_w_fn is None and osn is None
+                  and ops.tango_mid_supported(C, K))
+    st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn,
+                      apply_filter=not (fuse_mid or fuse_multi))
     Y, z_y, zn, W1 = st1["Y"], st1["z_y"], st1["zn"], st1["W1"]
     if mask_w_fn is not None:
         mask_w = mask_w_fn(Y, z_y, zn)
     R2 = None
     if fuse_mid:
         z_y, zn, Rss2, Rnn2 = ops.filter_sum_scm(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
+        R2 = (Rss2, Rnn2)
+    elif fuse_multi:
+        z_y, zn, Rss2, Rnn2 = ops.tango_mid(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
         R2 = (Rss2, Rnn2)
     z_s = z_n = None
     if have_sn and (diagnostics or mask_for_z in ("compressed", "use_oracle_zs")):
@@ -186,7 +193,7 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     # ---- step 2
     if R2 is not None:
         W2, _ = ops.mwf_solve(R2[0], R2[1], mu, filter_type, rank)
-        yf = ops.filter_sum(W2, Y, None, conj=True, n_fft=n_fft, out_layout=out_layout)
+        yf = ops.filter_sum(W2, Y, z_y if K > 1 else None, conj=True, n_fft=n_fft, out_layout=out_layout)
     else:
         yf, W2 = tango_step2(Y, z_y, mask_w, n_fft, mu, filter_type, rank, out_layout, z_rs=z_rs, z_rn=z_rn)
     out = {"yf": yf}

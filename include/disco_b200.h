@@ -124,6 +124,18 @@ DISCO_API int disco_filter_sum_scm(const void* W1, const void* Y, const float* m
                                    void* zn_out, int ref, void* Rss, void* Rnn, int n_grp, int C, int T, int n_fft,
                                    void* stream);
 
+/* ---- fused middle pass for multi-node arrays (K > 1) ---------------------------------------------------
+ * One pass over Y per utterance: z_k = w1_k^H y_k and zn_k = y_k[ref] - z_k for every node
+ * (reference tango.py:369-376), the exchange (every node sees the z of the others, tango.py:379-386)
+ * through shared memory, and the step-2 SCMs of every node under its mask_w (tango.py:431-440,
+ * mask_for_z = 'local').  Equivalent to disco_filter_sum + disco_masked_scm, reading Y once.
+ *   W1 [n_utt*K][F][C]; Y [n_utt*K][C][T][F]; mask_w [n_utt*K][T][F] (frame-major);
+ *   Z, ZN [n_utt][K][T][F] (ZN may be NULL); Rss, Rnn [n_utt*K][F][D][D], D = C + K - 1.
+ * Available for the (C, K) combinations disco_tango_mid_supported() reports. */
+DISCO_API int disco_tango_mid_supported(int C, int K);
+DISCO_API int disco_tango_mid(const void* W1, const void* Y, const float* mask_w, void* Z, void* ZN, int ref,
+                              void* Rss, void* Rnn, int n_utt, int K, int C, int T, int n_fft, void* stream);
+
 /* ---- per-bin MWF solve ---------------------------------------------------------------------------
  * Replaces intern_filter(Rxx, Rnn, mu, type, rank) (reference internal_formulas.py:31-81) for
  * n_mat matrices: Rss, Rnn [n_mat][D][D] complex64 -> W [n_mat][D], T1 [n_mat][D] complex64

@@ -73,7 +73,11 @@ def test_cfg3_shape_full_size_properties(dev):
     from disco_b200 import ops
     Y2 = ops.stft(y[:, 2:3].contiguous())
     yf2, _ = tango_step2(Y2, out["z_y"], mw[:, 2:3].contiguous(), node_sel=[2])
-    assert torch.equal(yf2[:, 0], out["yf"][:, 2])
+    # (two-kernel route vs the fused middle pass inside tango_batched: same mathematics, different summation order)
+    num = torch.linalg.norm(torch.view_as_real(yf2[:, 0] - out["yf"][:, 2]))
+    # this synthetic source is perfectly coherent across all 16 microphones, so the 7-channel GEVD amplifies
+    # the ~1e-7 differences between the two SCM summation orders by two to three orders of magnitude
+    assert (num / torch.linalg.norm(torch.view_as_real(out["yf"][:, 2]))).item() < 2e-4
     ref = tango_f64.offline_tango(y[5].cpu().numpy(), masks=(mz[5].cpu().numpy().transpose(0, 2, 1),
                                                              mw[5].cpu().numpy().transpose(0, 2, 1)))
     # step 2 solves a 7-channel GEVD on a perfectly coherent source: against EXACT arithmetic the float32

@@ -254,3 +254,30 @@ def test_solve_from_workspace_equals_two_step_route(dev, G, C):
     W2, t2, Rss2, Rnn2 = ops.mwf_solve_workspace(ws, G, C, L, want_scm=True)
     assert torch.equal(Y1, Y2) and torch.equal(Rss, Rss2) and torch.equal(Rnn, Rnn2)
     assert torch.equal(W1, W2) and torch.equal(t1, t2)
+
+
+@pytest.mark.parametrize("C,K", [(4, 4), (2, 8), (3, 2), (1, 3), (4, 8), (2, 6)])
+def test_fused_multi_node_mid_pass(dev, C, K):
+    """tango_mid (z of every node + step-2 SCMs of every node, one pass over Y) == filter_sum + masked_scm."""
+    from disco_b200 import ops
+    from oracle import tango_f64
+    assert ops.tango_mid_supported(C, K)
+    rng = np.random.default_rng(C * 10 + K)
+    B, T, F = 2, 83, 257
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, W = torch.from_numpy(cplx(B, K, C, T, F)).to(dev), torch.from_numpy(cplx(B, K, F, C)).to(dev)
+    m = torch.from_numpy(rng.uniform(size=(B, K, T, F)).astype(np.float32)).to(dev)
+    ref = C - 1
+    z, zn, Rss, Rnn = ops.tango_mid(W, Y, m, ref=ref)
+    z2, zn2 = ops.filter_sum(W, Y, None, conj=True, ref=ref)
+    Rss2, Rnn2 = ops.masked_scm(Y, m, z2)
+    assert rel_l2(_np(z), _np(z2)) < 1e-6 and rel_l2(_np(zn), _np(zn2)) < 1e-6
+    assert rel_l2(_np(Rss), _np(Rss2)) < 2e-6 and rel_l2(_np(Rnn), _np(Rnn2)) < 2e-6
+    # exact Hermitian mirrors, and the float64 oracle for one (utterance, node)
+    assert torch.equal(Rss, Rss.conj().transpose(-1, -2))
+    b, k = 1, K - 1
+    Yn, zall = _np(Y)[b, k], _np(z2)[b]
+    X = np.concatenate([Yn, zall[[j for j in range(K) if j != k]]], axis=0)
+    Rs, Rn = tango_f64.masked_scm(X.transpose(0, 2, 1), _np(m)[b, k].T)
+    assert rel_l2(_np(Rss)[b, k], Rs) < 3e-6 and rel_l2(_np(Rnn)[b, k], Rn) < 3e-6
+    assert not ops.tango_mid_supported(5, 2) and not ops.tango_mid_supported(4, 5)
