@@ -53,6 +53,7 @@ struct ScmArgs {
     int ref;
 };
 cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st);
+cudaError_t launch_masked_scm_wide(const ScmArgs& a, cudaStream_t st);   // D = 5..16 (scm_wide.cu)
 
 struct SolveArgs {
     const float2* Rss;   // [n_mat][D][D]
@@ -94,6 +95,7 @@ struct MidArgs {
     int B, K, C, T, F, ref;
 };
 cudaError_t launch_tango_mid(const MidArgs& a, cudaStream_t st);
+cudaError_t launch_tango_mid_v1(const MidArgs& a, cudaStream_t st);
 bool tango_mid_supported(int C, int K);
 
 struct IstftArgs {

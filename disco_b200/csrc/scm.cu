@@ -14,6 +14,7 @@
 // accumulators fit in registers for D up to 16; the TW time-ways are reduced through shared
 // memory at the end (fixed order -> deterministic), then scaled by 1/T and written with their
 // conjugate mirrors.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -299,6 +300,8 @@ static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
 
 cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st) {
     const int D = a.in.C + a.in.K - 1;
+    static const bool use_v1 = getenv("DISCO_SCM_V1") != nullptr;   // A/B timing of the previous generation
+    if (D >= 5 && !use_v1) return launch_masked_scm_wide(a, st);
     switch (D) {
         case 1: return launch_d<1>(a, st);
         case 2: return launch_d<2>(a, st);

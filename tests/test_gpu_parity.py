@@ -281,3 +281,41 @@ def test_fused_multi_node_mid_pass(dev, C, K):
     Rs, Rn = tango_f64.masked_scm(X.transpose(0, 2, 1), _np(m)[b, k].T)
     assert rel_l2(_np(Rss)[b, k], Rs) < 3e-6 and rel_l2(_np(Rnn)[b, k], Rn) < 3e-6
     assert not ops.tango_mid_supported(5, 2) and not ops.tango_mid_supported(4, 5)
+
+
+@pytest.mark.parametrize("n_fft,T", [(256, 301), (512, 130), (1024, 9)])
+def test_wide_scm_paths_long_and_short_sequences(dev, n_fft, T):
+    """The shared-memory-staged wide-channel kernels (D >= 5, fused multi-node pass) against float64 for frame
+    counts that give several / one / a partial tile, also in the Nyquist block (lanes <-> frames there)."""
+    from disco_b200 import ops
+    from oracle import tango_f64
+    rng = np.random.default_rng(T)
+    F = n_fft // 2 + 1
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    # K = 1, C = 8: fused z + SCM (D = 8) and the plain D = 8 SCM
+    B, C = 2, 8
+    Y, W = cplx(B, 1, C, T, F), cplx(B, 1, F, C)
+    m = rng.uniform(size=(B, 1, T, F)).astype(np.float32)
+    Yd, Wd, md = (torch.from_numpy(a).to(dev) for a in (Y, W, m))
+    z, zn, Rss, Rnn = ops.filter_sum_scm(Wd, Yd, md, ref=2, n_fft=n_fft)
+    Rss2, Rnn2 = ops.masked_scm(Yd, md, None, n_fft=n_fft)
+    assert torch.equal(Rss, Rss2) and torch.equal(Rnn, Rnn2)
+    zr = np.einsum("bkfc,bkctf->bktf", W.conj(), Y)
+    assert rel_l2(_np(z), zr) < 1e-6 and rel_l2(_np(zn), Y[:, :, 2] - zr) < 1e-6
+    for b in range(B):
+        Rs, Rn = tango_f64.masked_scm(Y[b, 0].transpose(0, 2, 1), m[b, 0].T)
+        assert rel_l2(_np(Rss)[b, 0], Rs) < 2e-6 and rel_l2(_np(Rnn)[b, 0], Rn) < 2e-6
+        assert rel_l2(_np(Rss)[b, 0, F - 1], Rs[F - 1]) < 2e-6          # the Nyquist bin on its own
+    # K = 4, C = 4: fused middle pass (D = 7) against the two-kernel route and float64
+    B, K, C = 2, 4, 4
+    Y, W = cplx(B, K, C, T, F), cplx(B, K, F, C)
+    m = rng.uniform(size=(B, K, T, F)).astype(np.float32)
+    Yd, Wd, md = (torch.from_numpy(a).to(dev) for a in (Y, W, m))
+    z, zn, Rss, Rnn = ops.tango_mid(Wd, Yd, md, ref=0, n_fft=n_fft)
+    zr = np.einsum("bkfc,bkctf->bktf", W.conj(), Y)
+    assert rel_l2(_np(z), zr) < 1e-6 and rel_l2(_np(zn), Y[:, :, 0] - zr) < 1e-6
+    for b, k in [(0, 0), (1, 2), (1, 3)]:
+        X = np.concatenate([Y[b, k], zr[b][[j for j in range(K) if j != k]]], axis=0)
+        Rs, Rn = tango_f64.masked_scm(X.transpose(0, 2, 1), m[b, k].T)
+        assert rel_l2(_np(Rss)[b, k], Rs) < 3e-6 and rel_l2(_np(Rnn)[b, k], Rn) < 3e-6
+        assert rel_l2(_np(Rss)[b, k, F - 1], Rs[F - 1]) < 3e-6
