@@ -39,6 +39,8 @@ SIGNATURES = {
     "disco_filter_sum": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int_p, c_int, c_void_p]),
     "disco_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "disco_band_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_int, c_int,
+                                 c_void_p]),
     "disco_transpose_c64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "disco_transpose_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "disco_apply_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -376,6 +376,25 @@ int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft
     return 0;
 }
 
+int disco_band_stats(const float* x, const float* sel, const double* ba, double* stats, int n_sig, int length,
+                     long long row_stride, int n_band, int order, void* stream) {
+    if (!x || !ba || !stats || n_sig < 1 || length < 1 || n_band < 1 || row_stride < length)
+        return fail(DISCO_ERR_INVALID, "bad arguments");
+    if (order != 2 && order != 4 && order != 8 && order != 16)
+        return fail(DISCO_ERR_UNSUPPORTED, "filter order must be 2, 4, 8 or 16");
+    BankArgs a;
+    a.x = x;
+    a.sel = sel;
+    a.ba = ba;
+    a.stats = stats;
+    a.n_sig = n_sig;
+    a.L = length;
+    a.n_band = n_band;
+    a.ldx = row_stride;
+    CU(launch_band_stats(a, order, (cudaStream_t)stream), "band_stats launch");
+    return 0;
+}
+
 int disco_transpose_c64(const void* in, void* out, int batch, int rows, int cols, void* stream) {
     if (!in || !out) return fail(DISCO_ERR_INVALID, "null pointer");
     CU(launch_transpose_c64((const float2*)in, (float2*)out, batch, rows, cols, (cudaStream_t)stream),

@@ -98,6 +98,17 @@ cudaError_t launch_tango_mid(const MidArgs& a, cudaStream_t st);
 cudaError_t launch_tango_mid_v1(const MidArgs& a, cudaStream_t st);
 bool tango_mid_supported(int C, int K);
 
+// IIR filter bank + band statistics (filterbank.cu; reference metrics.py fw_snr / fw_sd).
+struct BankArgs {
+    const float* x;      // [n_sig] rows of L samples, row stride ldx
+    const float* sel;    // optional, same layout: statistics over samples with sel != 0 (else: output != 0)
+    const double* ba;    // [n_band][2][order + 1]: numerator b, then denominator a
+    double* stats;       // [n_sig][n_band][3]: count, sum, sum of squares of the selected filter outputs
+    int n_sig, L, n_band;
+    long long ldx;
+};
+cudaError_t launch_band_stats(const BankArgs& a, int order, cudaStream_t st);
+
 struct IstftArgs {
     const float2* Y;     // [n_sig][T][F] frame-major complex64
     float* x;            // [n_sig][L]

@@ -270,6 +270,39 @@ def istft(Y, length, n_fft=512):
     return x
 
 
+def band_stats(x, ba, sel=None):
+    """IIR filter bank + statistics of every band's output (reference metrics.py:96-110: lfilter, then np.var of
+    the selected samples).  x [..., L] float32 (a time slice of a contiguous tensor is taken in place),
+    ba [n_band, 2, order+1] float64 (b, a), sel optional like x -> stats [..., n_band, 3] float64: count, sum,
+    sum of squares of the selected filter outputs."""
+    for t, name in ((x, "x"), (sel, "sel")):
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise TypeError("%s must be a CUDA tensor (disco_b200 has no CPU path)" % name)
+        if t.dtype != torch.float32:
+            raise TypeError("%s must be float32" % name)
+    L, lead = x.shape[-1], tuple(x.shape[:-1])
+    xv = x.reshape(-1, L)                      # a view when the rows are equally spaced
+    if xv.stride(1) != 1 or (xv.shape[0] > 1 and xv.stride(0) < L):
+        xv = xv.contiguous()
+    ld = xv.stride(0) if xv.shape[0] > 1 else L
+    sv = None
+    if sel is not None:
+        if tuple(sel.shape) != tuple(x.shape):
+            raise ValueError("sel must have the shape of x")
+        sv = torch.empty_strided(xv.shape, (ld, 1), dtype=torch.float32, device=x.device)
+        sv.copy_(sel.reshape(-1, L))
+    ba = ba.to(device=x.device, dtype=torch.float64).contiguous()
+    if ba.dim() != 3 or ba.shape[1] != 2:
+        raise ValueError("ba must be [n_band, 2, order + 1]")
+    n_band, order = ba.shape[0], ba.shape[2] - 1
+    stats = torch.empty(lead + (n_band, 3), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().disco_band_stats(_ptr(xv), _ptr(sv) if sv is not None else None, _ptr(ba), _ptr(stats),
+                                            xv.shape[0], L, int(ld), n_band, order, _stream()))
+    return stats
+
+
 def transpose_last2(a):
     """[..., R, C] -> [..., C, R] (contiguous) for complex64 / float32 device tensors."""
     R, Cc = a.shape[-2:]

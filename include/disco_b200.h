@@ -165,6 +165,18 @@ DISCO_API int disco_filter_sum(const void* W, int conj_w, const void* Y, const v
  *   Y [n_sig][T][F] complex64 (frame-major) -> x [n_sig][length] float32 */
 DISCO_API int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft, void* stream);
 
+/* ---- IIR filter bank + band statistics -------------------------------------------------------------
+ * Replaces, for every band i of a filter bank, `y = scipy.signal.lfilter(b[i], a[i], x)` followed by the
+ * statistics np.var needs, as the reference's frequency-weighted metrics do per third-octave band
+ * (metrics.py:96-110 fw_snr, :264-270 fw_sd).  Float64 direct form II transposed.
+ *   x     [n_sig] rows of `length` float32 samples, `row_stride` elements apart
+ *   sel   NULL: statistics over the outputs that are != 0 (metrics.py:100 `s_f[i][s_f[i] != 0]`);
+ *         else same layout as x: over the samples with sel != 0 (metrics.py:102 `[vad_tar != 0]`)
+ *   ba    [n_band][2][order + 1] float64: numerator, then denominator; order in {2, 4, 8, 16}
+ *   stats [n_sig][n_band][3] float64 out: count, sum, sum of squares */
+DISCO_API int disco_band_stats(const float* x, const float* sel, const double* ba, double* stats, int n_sig, int length,
+                     long long row_stride, int n_band, int order, void* stream);
+
 /* ---- layout helpers -------------------------------------------------------------------------------
  * out[b][c][r] = in[b][r][c] for `batch` planes (complex64 / float32).  Used at the Python
  * boundary to move between the reference (F, T) layout and the native (T, F) layout. */

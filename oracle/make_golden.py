@@ -181,6 +181,45 @@ def main():
                                                           frame_to_pred="mid", frames_lost=lost)[:3].numpy()
     np.savez_compressed(os.path.join(OUT, "crnn_kat.npz"), **blob)
     print("CRNN KATs written")
+    metrics_kat(ref)
+
+
+def metrics_kat(ref):
+    """Time-domain metrics of the reference (disco_theque/metrics.py) on seeded signals: fw_snr, fw_sd (with
+    the restated third-party OctaveBand injected, oracle/octave_np.py), snr, delta_snr, sd, si_sdr, and the
+    filter-bank coefficients of sigproc_utils.third_octave_filterbank."""
+    rng = np.random.default_rng(11)
+    L, fs = 12000, 16000
+    colour = np.exp(-np.arange(24) / 4.0) * rng.standard_normal(24)
+    s = np.stack([np.convolve(rng.standard_normal(L + 23), colour, "valid") * g for g in (0.1, 0.02, 0.3)])
+    n = rng.standard_normal((3, L)) * np.array([[0.05], [0.05], [0.01]])
+    s[1, :700] = 0.0                      # leading zeros: exactly-zero filter outputs are excluded (metrics.py:100)
+    n[2, :300] = 0.0
+    s, n = s.astype(np.float32), n.astype(np.float32)
+    est = (0.8 * s + 0.3 * n).astype(np.float32)
+    vad = (np.abs(s) > 0.5 * np.std(s, axis=1, keepdims=True)).astype(np.float64)
+    m = ref.metrics
+    blob = {"s": s, "n": n, "est": est, "vad": vad, "fs": fs}
+    for i in range(3):
+        fq, mean, F = m.fw_snr(s[i], n[i], fs)
+        blob["fw_snr_fq_%d" % i], blob["fw_snr_mean_%d" % i] = fq, mean
+        fq, mean, _ = m.fw_snr(s[i], n[i], fs, vad_tar=vad[i], vad_noi=vad[i])
+        blob["fw_snr_vad_fq_%d" % i], blob["fw_snr_vad_mean_%d" % i] = fq, mean
+        fq, mean, _ = m.fw_snr(s[i], n[i], fs, clipping=0, db=False)
+        blob["fw_snr_lin_fq_%d" % i], blob["fw_snr_lin_mean_%d" % i] = fq, mean
+        fq, mean, _ = m.fw_sd(est[i], s[i], fs)
+        blob["fw_sd_fq_%d" % i], blob["fw_sd_mean_%d" % i] = fq, mean
+        blob["snr_%d" % i] = m.snr(s[i], n[i])
+        blob["sd_%d" % i] = m.sd(est[i], s[i])
+        blob["delta_snr_%d" % i] = m.delta_snr(0.8 * s[i], 0.3 * n[i], s[i], n[i])
+        blob["si_sdr_%d" % i] = m.si_sdr(s[i].astype(np.float64), est[i].astype(np.float64))
+    blob["F"] = F
+    b, a = ref.third_octave_filterbank(F, fs, order=4)
+    blob["bank_b4"], blob["bank_a4"] = b, a
+    fq, mean, F8 = m.fw_snr(s[0], n[0], 8000)
+    blob["fw_snr8k_fq"], blob["fw_snr8k_mean"], blob["F8k"] = fq, mean, F8
+    np.savez_compressed(os.path.join(OUT, "metrics_kat.npz"), **blob)
+    print("metrics KATs written")
 
 
 if __name__ == "__main__":

@@ -62,7 +62,8 @@ def load():
     mpl.pyplot = _stub("matplotlib.pyplot")
     mpl.patches = _stub("matplotlib.patches", Rectangle=object, Circle=object)
     ac = _stub("acoustics")
-    ac.signal = _stub("acoustics.signal", OctaveBand=object)
+    from oracle import octave_np
+    ac.signal = _stub("acoustics.signal", OctaveBand=octave_np.OctaveBand)   # restated third party
     me = _stub("mir_eval")
     me.separation = _stub("mir_eval.separation", bss_eval_sources=_nope)
     ps = _stub("pystoi")
@@ -87,6 +88,7 @@ def load():
     formulas = importlib.import_module("disco_theque.se_utils.internal_formulas")
     sigproc = importlib.import_module("disco_theque.sigproc_utils")
     se_utils = importlib.import_module("disco_theque.speech_enhancement.utils")
+    metrics = importlib.import_module("disco_theque.metrics")
 
     ns = types.SimpleNamespace(
         tango=tango,
@@ -102,6 +104,8 @@ def load():
         vad_oracle_batch=sigproc.vad_oracle_batch,
         prepare_data=se_utils.prepare_data,
         build_crnn=crnn.build_crnn,
+        metrics=metrics,
+        third_octave_filterbank=sigproc.third_octave_filterbank,
     )
     _cached = ns
     return ns

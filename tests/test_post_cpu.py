@@ -17,3 +17,28 @@ def test_si_sdr_reference_doctests():
     both = si_sdr(np.stack([reference, reference]), np.stack([reference * 2 + 1, reference + 0.5]))
     assert np.allclose(both.numpy(), [6.3704606, 6.3704606], atol=1e-6)
     assert abs(snr_db(np.ones(10) * 2.0, np.ones(10)).item() - 10 * np.log10(4.0)) < 1e-12
+
+
+def test_third_octave_filterbank_matches_reference_coefficients():
+    """Own Butterworth band-pass design == the reference's sigproc_utils.third_octave_filterbank (scipy.signal.butter
+    on acoustics' band edges), golden coefficients from the reference run (tests/golden/metrics_kat.npz)."""
+    import os
+    from disco_b200 import post
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_kat.npz"))
+    F, I = post.third_octave_bands(16000)
+    assert np.array_equal(F, g["F"]) and len(I) == 17
+    assert np.array_equal(post.third_octave_bands(8000)[0], g["F8k"])
+    b, a = post.third_octave_filterbank(F, 16000, order=4)
+    for got, ref in ((b, g["bank_b4"]), (a, g["bank_a4"])):
+        assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=1, keepdims=True)) < 1e-13
+
+
+def test_octave_band_restatement_known_values():
+    """IEC 61260-1 base-10 third-octave bands: 1 kHz band = [10**2.95, 10**3.05] Hz, 160 Hz nominal -> 10**2.2."""
+    from oracle.octave_np import OctaveBand
+    ob = OctaveBand(center=1000, fraction=3)
+    assert abs(ob.lower.item() - 10 ** 2.95) < 1e-9 and abs(ob.upper.item() - 10 ** 3.05) < 1e-9
+    ob = OctaveBand(center=160, fraction=3)
+    assert abs(ob.center.item() - 10 ** 2.2) < 1e-9
+    ob = OctaveBand(center=[6300, 8000], fraction=3)
+    assert np.allclose(ob.center, [10 ** 3.8, 10 ** 3.9])
