@@ -285,9 +285,7 @@ int disco_tango_mid(const void* W1, const void* Y, const float* mask_w, void* Z,
     a.T = T;
     a.F = n_fft / 2 + 1;
     a.ref = ref;
-    static const bool use_v1 = getenv("DISCO_MID_V1") != nullptr;   // A/B timing of the previous generation
-    CU(use_v1 ? launch_tango_mid_v1(a, (cudaStream_t)stream) : launch_tango_mid(a, (cudaStream_t)stream),
-       "tango_mid launch");
+    CU(launch_tango_mid(a, (cudaStream_t)stream), "tango_mid launch");
     return 0;
 }
 

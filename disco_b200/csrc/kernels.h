@@ -95,7 +95,6 @@ struct MidArgs {
     int B, K, C, T, F, ref;
 };
 cudaError_t launch_tango_mid(const MidArgs& a, cudaStream_t st);
-cudaError_t launch_tango_mid_v1(const MidArgs& a, cudaStream_t st);
 bool tango_mid_supported(int C, int K);
 
 // IIR filter bank + band statistics (filterbank.cu; reference metrics.py fw_snr / fw_sd).

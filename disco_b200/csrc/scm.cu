@@ -1,5 +1,6 @@
-// Mask-weighted spatial covariance matrices of D = C + K - 1 channel spectra that are already
-// in HBM (step 2 of Tango: own microphones + compressed signals of the other nodes).
+// Mask-weighted spatial covariance matrices of D = C + K - 1 <= 4 channel spectra that are already
+// in HBM (step 2 of Tango: own microphones + compressed signals of the other nodes).  Wider stacks
+// (D = 5..16) use the shared-memory-staged engine of scm_wide.cu.
 //
 // Replaces the second triple loop of the reference (tango.py:431-440):
 //   in_to_phi_s = concat(m * Y_k, m * z_others), in_to_phi_n = concat((1-m) * Y_k, (1-m) * z_others)
@@ -9,12 +10,10 @@
 // Data are frame-major ([.., T, F], F contiguous), so a warp covers 32 consecutive bins of one
 // frame with coalesced 8-byte loads and every thread owns one bin: no shuffles are needed, the
 // time reduction is a register accumulation.  A CTA owns (group, 32-bin block) for ALL frames:
-//   threads = 32 bins x NPART pair-partitions x TW time-ways
-// The D(D+1)/2 Hermitian pairs are dealt round-robin to NPART warps-uniform partitions so the
-// accumulators fit in registers for D up to 16; the TW time-ways are reduced through shared
-// memory at the end (fixed order -> deterministic), then scaled by 1/T and written with their
-// conjugate mirrors.
-#include <stdlib.h>
+//   threads = 32 bins x TW = 8 time-ways
+// At D <= 4 the 2 x D(D+1)/2 accumulators AND two software-pipelined frames of operands fit in
+// registers; the TW time-ways are reduced through shared memory at the end (fixed order ->
+// deterministic), then scaled by 1/T and written with their conjugate mirrors.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,7 +22,7 @@ namespace disco {
 template <int D>
 struct ScmGeom {
     static constexpr int NPAIR = D * (D + 1) / 2;
-    static constexpr int NPART = D <= 4 ? 1 : (D <= 6 ? 2 : (D <= 9 ? 4 : 8));
+    static constexpr int NPART = 1;   // all pairs in one thread (the partitioned variants live in scm_wide.cu)
     static constexpr int NPP = (NPAIR + NPART - 1) / NPART;  // pairs per partition
     static constexpr int TW = 8 / NPART;
     static constexpr int THREADS = 256;
@@ -130,70 +129,53 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
             m = 1.f;
         }
     };
-    // Software pipeline over time: the loads of the next round are in flight while this round's two
-    // frames are consumed.  Small D keeps two extra register buffers (loads issued straight into them);
-    // wide D reloads into the same pair after consuming it, which costs no extra registers.
+    // Software pipeline over time: the loads of the next round are in flight (issued straight into two
+    // extra register buffers) while this round's two frames are consumed.
     constexpr int TS = G::TW;
     float2 ya[D], yb[D];
     float ma, mb;
     int t = tw;
     load1(t, ya, ma);
     load1(t + TS, yb, mb);
-    if constexpr (D <= 4) {
-        for (; t + 3 * TS < T; t += 2 * TS) {   // both frames of this round and of the next exist
-            float2 yc[D], yd[D];
-            float mc, md;
+    for (; t + 3 * TS < T; t += 2 * TS) {   // both frames of this round and of the next exist
+        float2 yc[D], yd[D];
+        float mc, md;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                yc[d] = ch[d][(t + 2 * TS) * F];
-                yd[d] = ch[d][(t + 3 * TS) * F];
-            }
-            mc = mrow ? mrow[(t + 2 * TS) * mstride] : 1.f;
-            md = mrow ? mrow[(t + 3 * TS) * mstride] : 1.f;
-            point(ya, ma, t);
-            point(yb, mb, t + TS);
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                ya[d] = yc[d];
-                yb[d] = yd[d];
-            }
-            ma = mc;
-            mb = md;
+        for (int d = 0; d < D; ++d) {
+            yc[d] = ch[d][(t + 2 * TS) * F];
+            yd[d] = ch[d][(t + 3 * TS) * F];
         }
-        for (; t < T; t += 2 * TS) {            // tail rounds (predicated loads)
-            float2 yc[D], yd[D];
-            float mc, md;
-            load1(t + 2 * TS, yc, mc);
-            load1(t + 3 * TS, yd, md);
-            point(ya, ma, t);
-            if (t + TS < T) point(yb, mb, t + TS);
+        mc = mrow ? mrow[(t + 2 * TS) * mstride] : 1.f;
+        md = mrow ? mrow[(t + 3 * TS) * mstride] : 1.f;
+        point(ya, ma, t);
+        point(yb, mb, t + TS);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                ya[d] = yc[d];
-                yb[d] = yd[d];
-            }
-            ma = mc;
-            mb = md;
+        for (int d = 0; d < D; ++d) {
+            ya[d] = yc[d];
+            yb[d] = yd[d];
         }
-    } else {
-        for (; t < T; t += 2 * TS) {
-            float2 y0[D], y1[D];
+        ma = mc;
+        mb = md;
+    }
+    for (; t < T; t += 2 * TS) {            // tail rounds (predicated loads)
+        float2 yc[D], yd[D];
+        float mc, md;
+        load1(t + 2 * TS, yc, mc);
+        load1(t + 3 * TS, yd, md);
+        point(ya, ma, t);
+        if (t + TS < T) point(yb, mb, t + TS);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                y0[d] = ya[d];
-                y1[d] = yb[d];
-            }
-            const float m0 = ma, m1 = mb;
-            load1(t + 2 * TS, ya, ma);
-            load1(t + 3 * TS, yb, mb);
-            point(y0, m0, t);
-            if (t + TS < T) point(y1, m1, t + TS);
+        for (int d = 0; d < D; ++d) {
+            ya[d] = yc[d];
+            yb[d] = yd[d];
         }
+        ma = mc;
+        mb = md;
     }
 }
 
 template <int D, bool ZF, int FC>
-__global__ void __launch_bounds__(ScmGeom<D>::THREADS, (D <= 4 ? 2 : 1)) masked_scm_kernel(ScmArgs a) {
+__global__ void __launch_bounds__(ScmGeom<D>::THREADS, 2) masked_scm_kernel(ScmArgs a) {
     using G = ScmGeom<D>;
     extern __shared__ float2 red[];  // [NPART][NPP][2][32]
     const int lane = threadIdx.x & 31;
@@ -208,16 +190,7 @@ __global__ void __launch_bounds__(ScmGeom<D>::THREADS, (D <= 4 ? 2 : 1)) masked_
 #pragma unroll
     for (int q = 0; q < G::NPP; ++q) ps[q] = pn[q] = make_float2(0.f, 0.f);
 
-    switch (part) {  // warp-uniform: keeps the (i, j) of every accumulator compile-time
-        case 0: scm_accumulate<D, 0, ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 1: if (G::NPART > 1) scm_accumulate<D, (G::NPART > 1 ? 1 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 2: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 2 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 3: if (G::NPART > 2) scm_accumulate<D, (G::NPART > 2 ? 3 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 4: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 4 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 5: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 5 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        case 6: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 6 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-        default: if (G::NPART > 4) scm_accumulate<D, (G::NPART > 4 ? 7 : 0), ZF, FC>(a, grp, fc, active, tw, ps, pn); break;
-    }
+    scm_accumulate<D, 0, ZF, FC>(a, grp, fc, active, tw, ps, pn);
 
     // reduce the TW time-ways in fixed order: way w adds into way 0 through shared memory
     float2* mine = red + (size_t)part * G::NPP * 2 * 32;
@@ -285,40 +258,24 @@ static cudaError_t launch_dzf(const ScmArgs& a, cudaStream_t st) {
 template <int D, bool ZF>
 static cudaError_t launch_dz(const ScmArgs& a, cudaStream_t st) {
     // the 512-point STFT (F = 257) of small nodes is the hot configuration: compile-time row stride
-    if (D <= 4 && a.in.F == 257) return launch_dzf<D, ZF, (D <= 4 ? 257 : 0)>(a, st);
+    if (a.in.F == 257) return launch_dzf<D, ZF, 257>(a, st);
     return launch_dzf<D, ZF, 0>(a, st);
 }
 
 template <int D>
 static cudaError_t launch_d(const ScmArgs& a, cudaStream_t st) {
-    if (a.W1 != nullptr) {
-        if (D > 8) return cudaErrorInvalidValue;
-        return launch_dz<(D > 8 ? 1 : D), true>(a, st);
-    }
+    if (a.W1 != nullptr) return launch_dz<D, true>(a, st);
     return launch_dz<D, false>(a, st);
 }
 
 cudaError_t launch_masked_scm(const ScmArgs& a, cudaStream_t st) {
     const int D = a.in.C + a.in.K - 1;
-    static const bool use_v1 = getenv("DISCO_SCM_V1") != nullptr;   // A/B timing of the previous generation
-    if (D >= 5 && !use_v1) return launch_masked_scm_wide(a, st);
+    if (D >= 5) return launch_masked_scm_wide(a, st);
     switch (D) {
         case 1: return launch_d<1>(a, st);
         case 2: return launch_d<2>(a, st);
         case 3: return launch_d<3>(a, st);
         case 4: return launch_d<4>(a, st);
-        case 5: return launch_d<5>(a, st);
-        case 6: return launch_d<6>(a, st);
-        case 7: return launch_d<7>(a, st);
-        case 8: return launch_d<8>(a, st);
-        case 9: return launch_d<9>(a, st);
-        case 10: return launch_d<10>(a, st);
-        case 11: return launch_d<11>(a, st);
-        case 12: return launch_d<12>(a, st);
-        case 13: return launch_d<13>(a, st);
-        case 14: return launch_d<14>(a, st);
-        case 15: return launch_d<15>(a, st);
-        case 16: return launch_d<16>(a, st);
         default: return cudaErrorInvalidValue;
     }
 }
