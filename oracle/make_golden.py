@@ -182,6 +182,67 @@ def main():
     np.savez_compressed(os.path.join(OUT, "crnn_kat.npz"), **blob)
     print("CRNN KATs written")
     metrics_kat(ref)
+    post_generator_kat(ref)
+
+
+def make_post_dataset(root, seed=21, rirs=(1, 2), lengths=(6000, 5200), noise="fs", scene="living", case="train"):
+    """A tiny on-disk data set in the layout PostGenerator reads (post_generator.py:86-97): 16 convolved target
+    and 16 convolved noise channels per RIR, 16-bit PCM.  Shared by the golden generator and the tests."""
+    from disco_b200 import wav_io          # the WAV codec restatement (soundfile is absent)
+    rng = np.random.default_rng(seed)
+    base = os.path.join(root, scene, case, "wav_original", "cnv")
+    os.makedirs(os.path.join(base, "target"), exist_ok=True)
+    os.makedirs(os.path.join(base, "noise"), exist_ok=True)
+    for rir, L in zip(rirs, lengths):
+        src = rng.standard_normal(L + 31) * 0.1
+        for ch in range(1, 17):
+            h = rng.standard_normal(32) * np.exp(-np.arange(32) / 6.0)
+            wav_io.write(os.path.join(base, "target", "%d_S-1_Ch-%d.wav" % (rir, ch)), np.convolve(src, h, "valid") * 0.5, 16000)
+            Ln = L - 400 if rir % 2 == 0 else L            # a shorter noise file exercises the zero padding
+            wav_io.write(os.path.join(base, "noise", "%d_S-2_%s_Ch-%d.wav" % (rir, noise, ch)),
+                         rng.standard_normal(Ln) * 0.05, 16000)
+
+
+def post_generator_kat(ref):
+    """Outputs of the reference's PostGenerator.post_process (dataset_utils/post_generator.py) on the tiny data set,
+    with `soundfile` backed by disco_b200.wav_io (the only substitution)."""
+    import importlib
+    import sys
+    import tempfile
+    from disco_b200 import wav_io
+    sfm = sys.modules["soundfile"]
+    sfm.read, sfm.write = wav_io.read, wav_io.write
+    pg = importlib.import_module("disco_theque.dataset_utils.post_generator")
+    blob = {}
+    with tempfile.TemporaryDirectory() as root:
+        make_post_dataset(root)
+        np.random.seed(7)
+        gen = pg.PostGenerator(1, 2, "living", "fs", [0, 6], root, n_samples=[10, 2, 2])
+        gen.post_process()
+        out = os.path.join(root, "living", "train")
+        for rir in (1, 2):
+            blob["snr_%d" % rir] = np.load(os.path.join(out, "log", "snrs", "dry", "0-6", "%d_fs.npy" % rir))
+            digest_m, digest_s = [], []
+            for ch in range(1, 17):
+                m = np.load(os.path.join(out, "mask_processed", "0-6", "%d_fs_Ch-%d.npy" % (rir, ch)))
+                x = np.load(os.path.join(out, "stft_processed", "raw", "0-6", "mixture", "%d_fs_Ch-%d.npy" % (rir, ch)))
+                digest_m.append(float(np.sum(m.astype(np.float64))))
+                digest_s.append(float(np.sum(np.abs(x).astype(np.float64))))
+                if ch in (1, 7, 16):
+                    blob["mask_%d_%d" % (rir, ch)] = m
+                if ch == 7:
+                    blob["mix_%d_%d" % (rir, ch)] = x
+                    blob["noi_%d_%d" % (rir, ch)] = np.load(os.path.join(out, "stft_processed", "raw", "0-6", "noise", "%d_fs_Ch-%d.npy" % (rir, ch)))
+                    blob["tar_%d_%d" % (rir, ch)] = np.load(os.path.join(out, "stft_processed", "raw", "0-6", "target", "%d_Ch-%d.npy" % (rir, ch)))
+                    blob["abs_%d_%d" % (rir, ch)] = np.load(os.path.join(out, "stft_processed", "normed", "abs", "0-6", "mixture", "%d_fs_Ch-%d.npy" % (rir, ch)))
+                    blob["wavmix_%d_%d" % (rir, ch)] = wav_io.read(os.path.join(out, "wav_processed", "0-6", "mixture", "%d_fs_Ch-%d.wav" % (rir, ch)))[0]
+                    blob["wavnoi_%d_%d" % (rir, ch)] = wav_io.read(os.path.join(out, "wav_processed", "0-6", "noise", "%d_fs_Ch-%d.wav" % (rir, ch)))[0]
+            blob["mask_sums_%d" % rir], blob["mix_abs_sums_%d" % rir] = np.array(digest_m), np.array(digest_s)
+        tree = sorted(os.path.relpath(os.path.join(d, f), out) for d, _, fs in os.walk(out) for f in fs
+                      if "wav_original" not in d)
+        blob["tree"] = np.array(tree)
+    np.savez_compressed(os.path.join(OUT, "post_generator_kat.npz"), **blob)
+    print("PostGenerator KATs written (%d files in the tree)" % len(tree))
 
 
 def metrics_kat(ref):

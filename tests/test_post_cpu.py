@@ -42,3 +42,19 @@ def test_octave_band_restatement_known_values():
     assert abs(ob.center.item() - 10 ** 2.2) < 1e-9
     ob = OctaveBand(center=[6300, 8000], fraction=3)
     assert np.allclose(ob.center, [10 ** 3.8, 10 ** 3.9])
+
+
+def test_wav_codec_roundtrip(tmp_path):
+    """disco_b200.wav_io: PCM16 -> float = x / 32768, float -> PCM16 = rint(x * 32767) (libsndfile's rules)."""
+    from disco_b200 import wav_io
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5 / 32767, 2.5 / 32767, 0.123456], dtype=np.float64)
+    p = str(tmp_path / "a.wav")
+    wav_io.write(p, x, 16000)
+    y, fs = wav_io.read(p)
+    assert fs == 16000 and y.dtype == np.float32
+    want = np.array([0, 16384, -16384, 32767, -32767, 2, 2, 4045]) / 32768.0     # half to even: 1.5 -> 2, 2.5 -> 2
+    assert np.array_equal(y, want.astype(np.float32))
+    stereo = np.stack([x, -x], axis=1)
+    wav_io.write(p, stereo, 8000)
+    y2, fs2 = wav_io.read(p, dtype="float64")
+    assert fs2 == 8000 and y2.shape == (8, 2) and np.array_equal(y2[:, 1], -y2[:, 0])
