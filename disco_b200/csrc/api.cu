@@ -374,6 +374,60 @@ int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft
     return 0;
 }
 
+int disco_scm_recursive(const void* Y, const void* Z, const float* mask, const void* R0ss, const void* R0nn, void* Rss,
+                        void* Rnn, double lambda_cor, int block, int weight_power, int n_utt, int K, int C, int T,
+                        int n_fft, const int* node_sel, int n_sel, void* stream) {
+    OnlineArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    if (rc) return rc;
+    if (C + K - 1 > 8) return fail(DISCO_ERR_UNSUPPORTED, "recursive SCM: C + K - 1 must be <= 8");
+    if (!Rss || !Rnn || (!R0ss) != (!R0nn)) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (block < 1 || block > 64) return fail(DISCO_ERR_INVALID, "block must be 1..64 frames");
+    if (!(lambda_cor >= 0.0 && lambda_cor < 1.0)) return fail(DISCO_ERR_INVALID, "lambda_cor must be in [0, 1)");
+    if (weight_power != 1 && weight_power != 2) return fail(DISCO_ERR_INVALID, "weight_power must be 1 or 2");
+    a.mask = mask;
+    a.R0ss = (const float2*)R0ss;
+    a.R0nn = (const float2*)R0nn;
+    a.Rss = (float2*)Rss;
+    a.Rnn = (float2*)Rnn;
+    a.P = block;
+    a.J = (T + block - 1) / block;
+    a.power = weight_power;
+    double g = 1.0 - lambda_cor;
+    for (int k = 0; k < 64; ++k) {
+        a.gw[k] = (float)g;
+        g *= lambda_cor;
+    }
+    a.lam_block = (float)pow(lambda_cor, block);
+    a.lam_last = (float)pow(lambda_cor, T - (a.J - 1) * block);
+    CU(launch_scm_recursive(a, (cudaStream_t)stream), "scm_recursive launch");
+    return 0;
+}
+
+int disco_filter_sum_blocks(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
+                            int block, int lag, int n_utt, int K, int C, int T, int n_fft, const int* node_sel,
+                            int n_sel, void* stream) {
+    OnlineFilterArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    if (rc) return rc;
+    if (C + K - 1 > 8) return fail(DISCO_ERR_UNSUPPORTED, "block filter: C + K - 1 must be <= 8");
+    if (!W || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (block < 1 || block > 64 || lag < 0) return fail(DISCO_ERR_INVALID, "bad block / lag");
+    if (ref < 0 || ref >= C + K - 1) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    a.W = (const float2*)W;
+    a.conj_w = conj_w;
+    a.out = (float2*)out;
+    a.resid = (float2*)resid;
+    a.ref = ref;
+    a.P = block;
+    a.J = (T + block - 1) / block;
+    a.lag = lag;
+    CU(launch_filter_sum_blocks(a, (cudaStream_t)stream), "filter_sum_blocks launch");
+    return 0;
+}
+
 int disco_band_stats(const float* x, const float* sel, const double* ba, double* stats, int n_sig, int length,
                      long long row_stride, int n_band, int order, void* stream) {
     if (!x || !ba || !stats || n_sig < 1 || length < 1 || n_band < 1 || row_stride < length)

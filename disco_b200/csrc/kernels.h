@@ -97,6 +97,31 @@ struct MidArgs {
 cudaError_t launch_tango_mid(const MidArgs& a, cudaStream_t st);
 bool tango_mid_supported(int C, int K);
 
+// Recursive (online) SCMs and block-wise filtering (online.cu; reference internal_formulas.py:84-103).
+struct OnlineArgs {
+    CatArgs in;
+    const float* mask;      // [n_grp][T][F] frame-major, or null (all ones: plain smoothed SCM into Rss, Rnn = decay only)
+    const float2* R0ss;     // optional initial matrices [n_grp][F][D][D]
+    const float2* R0nn;
+    float2* Rss;            // [n_grp][J][F][D][D]: smoothed SCMs after the last frame of every block
+    float2* Rnn;
+    int P, J;               // frames per block, number of blocks = ceil(T / P)
+    int power;              // 2: weights m^2, (1-m)^2 (x = m y estimate, M = None); 1: m, 1-m (x = mixture, M = mask)
+    float lam_block, lam_last;   // lambda^P, lambda^(frames of the last block)
+    float gw[64];           // (1 - lambda) lambda^k, k = 0..P-1
+};
+cudaError_t launch_scm_recursive(const OnlineArgs& a, cudaStream_t st);
+
+struct OnlineFilterArgs {
+    CatArgs in;
+    const float2* W;        // [n_grp][J][F][D] one filter per block
+    int conj_w;
+    float2* out;            // [n_grp][T][F]
+    float2* resid;          // optional x[ref] - out
+    int ref, P, J, lag;     // frame t uses filter t / P - lag (pass-through of channel `ref` while that is < 0)
+};
+cudaError_t launch_filter_sum_blocks(const OnlineFilterArgs& a, cudaStream_t st);
+
 // IIR filter bank + band statistics (filterbank.cu; reference metrics.py fw_snr / fw_sd).
 struct BankArgs {
     const float* x;      // [n_sig] rows of L samples, row stride ldx

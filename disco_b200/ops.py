@@ -270,6 +270,65 @@ def istft(Y, length, n_fft=512):
     return x
 
 
+def _cat_dims(Y, Z, node_sel):
+    B, Ks, C, T, F = Y.shape
+    K = 1 if Z is None else Z.shape[1]
+    if Z is None:
+        return B * Ks, None, 1, K, C, T, F
+    _need(Z, torch.complex64, "Z")
+    sel, n_sel, _ = _sel(node_sel, K)
+    if Ks != n_sel:
+        raise ValueError("Y holds %d nodes, selection has %d" % (Ks, n_sel))
+    return B, sel, n_sel, K, C, T, F
+
+
+def scm_recursive(Y, mask, Z=None, lambda_cor=0.95, block=8, power=2, R0=None, n_fft=512, node_sel=None):
+    """Exponentially smoothed SCM pair, R <- lambda R + (1 - lambda) w x x^H per frame (reference
+    spatial_correlation_matrix, internal_formulas.py:84-103), sampled after every block of `block` frames.
+    Y [B, Ksel, C, T, F], Z [B, K, T, F] or None, mask [B, Ksel, T, F] or None, R0 = (R0ss, R0nn) [B, Ksel, F, D, D]
+    -> Rss, Rnn [B, Ksel, J, F, D, D], J = ceil(T / block)."""
+    _need(Y, torch.complex64, "Y")
+    if mask is not None:
+        _need(mask, torch.float32, "mask")
+    n_utt, sel, n_sel, K, C, T, F = _cat_dims(Y, Z, node_sel)
+    B, Ks = Y.shape[:2]
+    D = C + K - 1
+    if mask is not None and tuple(mask.shape) != (B, Ks, T, F):
+        raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), (B, Ks, T, F)))
+    J = (T + block - 1) // block
+    Rss = torch.empty((B, Ks, J, F, D, D), dtype=torch.complex64, device=Y.device)
+    Rnn = torch.empty_like(Rss)
+    r0s = r0n = None
+    if R0 is not None:
+        r0s, r0n = R0
+        for r in (r0s, r0n):
+            _need(r, torch.complex64, "R0")
+            if tuple(r.shape) != (B, Ks, F, D, D):
+                raise ValueError("R0 shape %s, expected %s" % (tuple(r.shape), (B, Ks, F, D, D)))
+    _lib.check(_lib.load().disco_scm_recursive(_ptr(Y), _ptr(Z), _ptr(mask), _ptr(r0s), _ptr(r0n), _ptr(Rss), _ptr(Rnn),
+                                               float(lambda_cor), int(block), int(power), n_utt, K, C, T, n_fft, sel,
+                                               n_sel, _stream()))
+    return Rss, Rnn
+
+
+def filter_sum_blocks(W, Y, Z=None, block=8, lag=1, conj=True, ref=0, n_fft=512, node_sel=None):
+    """One filter per block of frames: out[t] = W[t // block - lag]^H x[t] (pass-through of channel `ref` while no
+    filter exists yet).  W [B, Ksel, J, F, D] -> out, resid = x[ref] - out, [B, Ksel, T, F]."""
+    _need(W, torch.complex64, "W")
+    _need(Y, torch.complex64, "Y")
+    n_utt, sel, n_sel, K, C, T, F = _cat_dims(Y, Z, node_sel)
+    B, Ks = Y.shape[:2]
+    D, J = C + K - 1, (T + block - 1) // block
+    if tuple(W.shape) != (B, Ks, J, F, D):
+        raise ValueError("W shape %s, expected %s" % (tuple(W.shape), (B, Ks, J, F, D)))
+    out = torch.empty((B, Ks, T, F), dtype=torch.complex64, device=Y.device)
+    resid = torch.empty_like(out)
+    _lib.check(_lib.load().disco_filter_sum_blocks(_ptr(W), 1 if conj else 0, _ptr(Y), _ptr(Z), _ptr(out), _ptr(resid),
+                                                   int(ref), int(block), int(lag), n_utt, K, C, T, n_fft, sel, n_sel,
+                                                   _stream()))
+    return out, resid
+
+
 def band_stats(x, ba, sel=None):
     """IIR filter bank + statistics of every band's output (reference metrics.py:96-110: lfilter, then np.var of
     the selected samples).  x [..., L] float32 (a time slice of a contiguous tensor is taken in place),

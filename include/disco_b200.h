@@ -165,6 +165,25 @@ DISCO_API int disco_filter_sum(const void* W, int conj_w, const void* Y, const v
  *   Y [n_sig][T][F] complex64 (frame-major) -> x [n_sig][length] float32 */
 DISCO_API int disco_istft(const void* Y, float* x, int n_sig, int T, int length, int n_fft, void* stream);
 
+/* ---- recursive (online) statistics and block-wise filtering ------------------------------------------
+ * disco_scm_recursive evaluates, for every frame t and bin, the reference's one-frame update
+ *   spatial_correlation_matrix(Rxx, x, lambda_cor, M):  R <- lambda R + (1 - lambda) [M] x x^H
+ * (se_utils/internal_formulas.py:84-103) for the pair (R_ss, R_nn) on the concatenated channel view of
+ * disco_masked_scm, as a two-level scan, and returns the matrices after the last frame of every block of
+ * `block` frames (1..64):  Rss, Rnn [n_utt*n_sel][J][F][D][D], J = ceil(T / block), D = C + K - 1 <= 8.
+ *   weight_power 2: weights m^2 and (1-m)^2 (the caller would pass x = m y, (1-m) y with M = None);
+ *   weight_power 1: weights m and 1-m       (x = mixture, M = mask);   mask NULL: weight 1 into Rss, Rnn decays.
+ *   R0ss, R0nn: optional initial matrices [n_utt*n_sel][F][D][D] (NULL = zeros).
+ * disco_filter_sum_blocks applies one filter per block: frame t gets W[.., t / block - lag, ..]
+ * (lag = 1: the filter of the last completed block, strictly causal; while that index is negative the
+ * reference channel passes through), out = w^H x (conj_w = 1), resid = x[ref] - out (optional). */
+DISCO_API int disco_scm_recursive(const void* Y, const void* Z, const float* mask, const void* R0ss, const void* R0nn,
+                     void* Rss, void* Rnn, double lambda_cor, int block, int weight_power, int n_utt, int K, int C,
+                     int T, int n_fft, const int* node_sel, int n_sel, void* stream);
+DISCO_API int disco_filter_sum_blocks(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid,
+                     int ref, int block, int lag, int n_utt, int K, int C, int T, int n_fft, const int* node_sel,
+                     int n_sel, void* stream);
+
 /* ---- IIR filter bank + band statistics -------------------------------------------------------------
  * Replaces, for every band i of a filter bank, `y = scipy.signal.lfilter(b[i], a[i], x)` followed by the
  * statistics np.var needs, as the reference's frequency-weighted metrics do per third-octave band

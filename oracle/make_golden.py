@@ -183,6 +183,32 @@ def main():
     print("CRNN KATs written")
     metrics_kat(ref)
     post_generator_kat(ref)
+    online_kat(ref)
+
+
+def online_inputs(seed=31, D=3, F=129, T=37):
+    """Seeded spectra / mask of the online known-answer case (shared with the tests)."""
+    rng = np.random.default_rng(seed)
+    src = rng.standard_normal((F, T)) + 1j * rng.standard_normal((F, T))
+    steer = rng.standard_normal((D, F, 1)) + 1j * rng.standard_normal((D, F, 1))
+    X = (steer * src[None] + 0.3 * (rng.standard_normal((D, F, T)) + 1j * rng.standard_normal((D, F, T)))).astype(np.complex64)
+    mask = rng.uniform(0.05, 0.95, size=(F, T)).astype(np.float32)
+    return X, mask
+
+
+def online_kat(ref):
+    """Recursive MWF step as the per-frame composition of the REFERENCE's spatial_correlation_matrix and
+    intern_filter (oracle/online_np.py drives them): z, filters and smoothed SCM snapshots."""
+    from oracle import online_np
+    X, mask = online_inputs()
+    blob = {}
+    for tag, kw in (("p8l1", dict(block=8, lag=1)), ("p5l0", dict(block=5, lag=0)),
+                    ("p8l1pow1", dict(block=8, lag=1, power=1, lambda_cor=0.9))):
+        z, W, Rs, Rn = online_np.online_mwf(X, mask, ref.spatial_correlation_matrix, ref.intern_filter, **kw)
+        blob[tag + "_z"], blob[tag + "_W"] = z.astype(np.complex64), W.astype(np.complex64)
+        blob[tag + "_Rss"], blob[tag + "_Rnn"] = Rs[-2:].astype(np.complex64), Rn[-2:].astype(np.complex64)
+    np.savez_compressed(os.path.join(OUT, "online_kat.npz"), **blob)
+    print("online KATs written")
 
 
 def make_post_dataset(root, seed=21, rirs=(1, 2), lengths=(6000, 5200), noise="fs", scene="living", case="train"):

@@ -1,0 +1,108 @@
+"""Online (recursive) MWF kernels (csrc/online.cu, disco_b200/online.py) against the per-frame composition of the
+reference's spatial_correlation_matrix + intern_filter (tests/golden/online_kat.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "online_kat.npz")
+
+
+def rel(a, b):
+    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _to_dev(X, mask, dev):
+    """(D, F, T), (F, T) -> Y [1, 1, D, T, F], mask [1, 1, T, F] (frame-major)."""
+    Y = torch.from_numpy(np.ascontiguousarray(X.transpose(0, 2, 1))[None, None]).to(dev)
+    m = torch.from_numpy(np.ascontiguousarray(mask.T)[None, None]).to(dev)
+    return Y, m
+
+
+@pytest.mark.parametrize("tag,kw", [("p8l1", dict(block=8, lag=1)), ("p5l0", dict(block=5, lag=0)),
+                                    ("p8l1pow1", dict(block=8, lag=1, power=1, lambda_cor=0.9))])
+def test_online_step_matches_reference_composition(dev, tag, kw):
+    from disco_b200 import online
+    from oracle.make_golden import online_inputs
+    g = np.load(GOLD)
+    X, mask = online_inputs()
+    Y, m = _to_dev(X, mask, dev)
+    out = online.online_mwf(Y, m, None, n_fft=256, **kw)
+    J = out["W"].shape[2]
+    assert rel(out["Rss"][0, 0, J - 2:], g[tag + "_Rss"]) < 3e-6 and rel(out["Rnn"][0, 0, J - 2:], g[tag + "_Rnn"]) < 3e-6
+    # filters: scale-free comparison through the filtered signal; W itself to the solver's tolerance
+    assert rel(out["W"][0, 0], g[tag + "_W"]) < 2e-4
+    z = out["z"][0, 0].cpu().numpy().T                     # (F, T)
+    assert np.linalg.norm(np.abs(z) - np.abs(g[tag + "_z"])) / np.linalg.norm(np.abs(g[tag + "_z"])) < 1e-5
+    zn = out["zn"][0, 0].cpu().numpy().T
+    assert rel(zn, X[0] - z) < 1e-6
+
+
+def test_online_batched_concat_and_initial_matrices(dev):
+    """Batch / node axes, the [own mics ; z of the other nodes] view, a partial last block and R0."""
+    from disco_b200 import ops
+    from oracle import online_np, tango_np
+    rng = np.random.default_rng(4)
+    B, K, C, T, F = 2, 3, 2, 21, 129
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, Z = cplx(B, K, C, T, F), cplx(B, K, T, F)
+    m = rng.uniform(0.1, 0.9, size=(B, K, T, F)).astype(np.float32)
+    D = C + K - 1
+    R0 = np.tile(np.eye(D, dtype=np.complex64) * 0.01, (B, K, F, 1, 1))
+    Yd, Zd, md, R0d = (torch.from_numpy(a).to(dev) for a in (Y, Z, m, R0))
+    Rss, Rnn = ops.scm_recursive(Yd, md, Zd, lambda_cor=0.9, block=4, power=2, R0=(R0d, R0d.clone()), n_fft=256)
+    assert Rss.shape == (B, K, 6, F, D, D)
+    b, k = 1, 1
+    X = np.concatenate([Y[b, k], Z[b, [j for j in range(K) if j != k]]], axis=0).transpose(0, 2, 1)   # (D, F, T)
+    fsel = [0, 40, 128]
+    _, _, Rs, Rn = online_np.online_mwf(X[:, fsel], m[b, k].T[fsel], tango_np.spatial_correlation_matrix,
+                                        tango_np.intern_filter, lambda_cor=0.9, block=4,
+                                        R0=(R0[b, k][fsel], R0[b, k][fsel]))
+    got_s, got_n = Rss[b, k].cpu().numpy()[:, fsel], Rnn[b, k].cpu().numpy()[:, fsel]
+    assert np.linalg.norm(got_s - Rs) / np.linalg.norm(Rs) < 3e-6 and np.linalg.norm(got_n - Rn) / np.linalg.norm(Rn) < 3e-6
+    assert torch.equal(Rss, Rss.conj().transpose(-1, -2))
+    # block filter application with a lag: frame t uses W[t // 4 - 1]
+    W = torch.from_numpy(cplx(B, K, 6, F, D)).to(dev)
+    out, resid = ops.filter_sum_blocks(W, Yd, Zd, block=4, lag=1, ref=1, n_fft=256)
+    Wn = W.cpu().numpy()
+    for t in (0, 3, 4, 11, 20):
+        jw = t // 4 - 1
+        want = X[1, :, t] if jw < 0 else np.einsum("fd,df->f", Wn[b, k, jw].conj(), X[:, :, t])
+        assert np.linalg.norm(out[b, k, t].cpu().numpy() - want) / np.linalg.norm(want) < 1e-6
+        assert np.linalg.norm(resid[b, k, t].cpu().numpy() - (X[1, :, t] - want)) <= 1e-5 * np.linalg.norm(want) + 1e-6
+
+
+def test_online_tango_two_nodes_matches_oracle(dev):
+    """Two-step recursive Tango on time signals == the oracle composition (step 1 per node, exchange of z, step 2 on
+    [own mics ; z of the other node]) on a subset of bins."""
+    from disco_b200 import online
+    from disco_b200.synth import make_batch
+    from oracle import librosa_np, online_np, tango_np
+    B, K, C, L = 2, 2, 3, 8000
+    y, s, n = make_batch(B, K, C, L, seed0=700)
+    rng = np.random.default_rng(1)
+    T, F = 1 + L // 256, 257
+    mz = rng.uniform(0.1, 0.9, size=(B, K, T, F)).astype(np.float32)
+    mw = rng.uniform(0.1, 0.9, size=(B, K, T, F)).astype(np.float32)
+    on = online.online_tango(torch.from_numpy(y).to(dev), (torch.from_numpy(mz).to(dev), torch.from_numpy(mw).to(dev)),
+                             lambda_cor=0.9, block=4, lag=1)
+    assert on["yf"].shape == (B, K, T, F) and bool(torch.isfinite(torch.view_as_real(on["yf"])).all())
+    b, fsel = 1, [3, 100, 256]
+    Yk = [np.stack([librosa_np.stft(y[b, k, c]) for c in range(C)])[:, fsel] for k in range(K)]       # (C, f, T)
+    fn = (tango_np.spatial_correlation_matrix, tango_np.intern_filter)
+    z1 = [online_np.online_mwf(Yk[k], mz[b, k].T[fsel], *fn, lambda_cor=0.9, block=4, lag=1)[0] for k in range(K)]
+    for k in range(K):
+        X2 = np.concatenate([Yk[k], z1[1 - k][None]], axis=0)
+        yf = online_np.online_mwf(X2, mw[b, k].T[fsel], *fn, lambda_cor=0.9, block=4, lag=1)[0]
+        got1 = on["z_y"][b, k].cpu().numpy().T[fsel]
+        got2 = on["yf"][b, k].cpu().numpy().T[fsel]
+        assert np.linalg.norm(np.abs(got1) - np.abs(z1[k])) / np.linalg.norm(np.abs(z1[k])) < 1e-4
+        assert np.linalg.norm(np.abs(got2) - np.abs(yf)) / np.linalg.norm(np.abs(yf)) < 1e-4
