@@ -19,6 +19,7 @@
 // (own mics, then nodes < k, then nodes > k; concatenate_signals, tango.py:153-155).
 // For K > 4 the K nodes' SCMs are split over K/KS CTAs (adjacent in launch order, so the spectra they
 // share are L2 hits; each recomputes all z: C complex multiplies per value).
+#include <stdlib.h>
 #include "kernels.h"
 #include "scm_core.cuh"
 
@@ -197,13 +198,9 @@ __global__ void __launch_bounds__(32 * KS * NPART, MINB) tango_mid_kernel(MidArg
     }
 }
 
-template <int C, int K>
-static cudaError_t launch_ck(const MidArgs& a, cudaStream_t st) {
+template <int C, int K, int KS, int NPART>
+static cudaError_t launch_cfg(const MidArgs& a, cudaStream_t st) {
     constexpr int D = C + K - 1;
-    constexpr int NPAIR = D * (D + 1) / 2;
-    constexpr int NPART = NPAIR <= 16 ? 1 : (NPAIR <= 32 ? 2 : (NPAIR <= 48 ? 3 : 4));
-    // nodes per CTA: all of them while the CTA stays at <= 12 warps, else a divisor of K
-    constexpr int KS = K * NPART <= 12 ? K : (K % 4 == 0 && 4 * NPART <= 12 ? 4 : (K % 2 == 0 ? 2 : 1));
     constexpr int NS = MidCfg<C, K, KS, NPART, 4>::SMEM <= 76 * 1024 ? 4 : 3;
     using G = MidCfg<C, K, KS, NPART, NS>;
     constexpr int THREADS = 32 * G::NW;
@@ -216,6 +213,22 @@ static cudaError_t launch_ck(const MidArgs& a, cudaStream_t st) {
     dim3 grid(K / KS, (a.F + 31) / 32, a.B);
     kern<<<grid, THREADS, G::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int C, int K>
+static cudaError_t launch_ck(const MidArgs& a, cudaStream_t st) {
+    constexpr int D = C + K - 1;
+    constexpr int NPAIR = D * (D + 1) / 2;
+    constexpr int NPART = NPAIR <= 16 ? 1 : (NPAIR <= 32 ? 2 : (NPAIR <= 48 ? 3 : 4));
+    // nodes per CTA: all of them while the CTA stays at <= 12 warps, else a divisor of K
+    constexpr int KS = K * NPART <= 12 ? K : (K % 4 == 0 && 4 * NPART <= 12 ? 4 : (K % 2 == 0 ? 2 : 1));
+    if constexpr (C == 2 && K == 8) {   // experiment switch (timing only): alternative CTA shapes
+        static const int alt = getenv("DISCO_MID_ALT") ? atoi(getenv("DISCO_MID_ALT")) : 0;
+        if (alt == 1) return launch_cfg<C, K, 2, 3>(a, st);
+        if (alt == 2) return launch_cfg<C, K, 2, 4>(a, st);
+        if (alt == 3) return launch_cfg<C, K, 4, 4>(a, st);
+    }
+    return launch_cfg<C, K, KS, NPART>(a, st);
 }
 
 // Supported (C, K) combinations; anything else reports cudaErrorNotSupported and the caller uses the
