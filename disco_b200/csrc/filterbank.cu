@@ -2,7 +2,7 @@
 // (reference disco_theque/metrics.py:96-110 fw_snr and :264-270 fw_sd: per third-octave band
 // `scipy.signal.lfilter(b[i], a[i], x)` on the whole signal, then `np.var` of the selected output samples).
 //
-// The recurrence (direct form II transposed, float64, the arithmetic of scipy's lfilter) is serial in
+// The recurrence (direct form II transposed, float64, the arithmetic AND rounding sequence of scipy's lfilter) is serial in
 // time, so the parallelism is (signal, band): lanes <-> 32 different signals, warps <-> bands.  A CTA
 // streams chunks of the 32 signals through a double-buffered, padded shared-memory tile (coalesced
 // global loads, conflict-free per-lane reads) that all its band-warps share; each thread keeps its
@@ -26,14 +26,14 @@ __global__ void __launch_bounds__(32 * kBankWarps) band_stats_kernel(BankArgs a)
     const bool live = band < a.n_band;            // warp-uniform
     const bool has_sel = a.sel != nullptr;
 
-    double b[NC], am[NC], z[NC - 1];
+    double b[NC], a_[NC], z[NC - 1];
     {
         const double* q = a.ba + (size_t)(live ? band : 0) * 2 * NC;
         const double a0 = q[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             b[i] = q[i] / a0;                     // lfilter normalises by a[0]
-            am[i] = -q[NC + i] / a0;
+            a_[i] = q[NC + i] / a0;
         }
 #pragma unroll
         for (int i = 0; i < NC - 1; ++i) z[i] = 0.0;
@@ -64,10 +64,14 @@ __global__ void __launch_bounds__(32 * kBankWarps) band_stats_kernel(BankArgs a)
             const int nval = min(kBankChunk, a.L - c * kBankChunk);
             for (int n = 0; n < nval; ++n) {
                 const double x = (double)xs[buf][lane][n];
-                const double y = fma(b[0], x, z[0]);
+                // scipy's evaluation order with every product and sum rounded separately (no FMA contraction):
+                // the order-8 band-passes of the lowest bands amplify rounding differences by ~1e10, so matching
+                // the reference's numbers means matching its arithmetic (x86-64 SciPy builds do not contract)
+                const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
 #pragma unroll
-                for (int i = 0; i < NC - 2; ++i) z[i] = fma(am[i + 1], y, fma(b[i + 1], x, z[i + 1]));
-                z[NC - 2] = fma(am[NC - 1], y, b[NC - 1] * x);
+                for (int i = 0; i < NC - 2; ++i)
+                    z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, b[i + 1])), __dmul_rn(y, a_[i + 1]));
+                z[NC - 2] = __dsub_rn(__dmul_rn(x, b[NC - 1]), __dmul_rn(y, a_[NC - 1]));
                 const bool take = has_sel ? (ss[buf][lane][n] != 0.f) : (y != 0.0);
                 if (take) {
                     cnt += 1.0;

@@ -19,7 +19,6 @@
 // (own mics, then nodes < k, then nodes > k; concatenate_signals, tango.py:153-155).
 // For K > 4 the K nodes' SCMs are split over K/KS CTAs (adjacent in launch order, so the spectra they
 // share are L2 hits; each recomputes all z: C complex multiplies per value).
-#include <stdlib.h>
 #include "kernels.h"
 #include "scm_core.cuh"
 
@@ -220,14 +219,9 @@ static cudaError_t launch_ck(const MidArgs& a, cudaStream_t st) {
     constexpr int D = C + K - 1;
     constexpr int NPAIR = D * (D + 1) / 2;
     constexpr int NPART = NPAIR <= 16 ? 1 : (NPAIR <= 32 ? 2 : (NPAIR <= 48 ? 3 : 4));
-    // nodes per CTA: all of them while the CTA stays at <= 12 warps, else a divisor of K
+    // nodes per CTA: all of them while the CTA stays at <= 12 warps, else a divisor of K (measured at C = 2, K = 8:
+    // KS 4 / NPART 3 1.81 ms; KS 2 / NPART 3 2.41; KS 2 / NPART 4 2.00; KS 4 / NPART 4 2.01)
     constexpr int KS = K * NPART <= 12 ? K : (K % 4 == 0 && 4 * NPART <= 12 ? 4 : (K % 2 == 0 ? 2 : 1));
-    if constexpr (C == 2 && K == 8) {   // experiment switch (timing only): alternative CTA shapes
-        static const int alt = getenv("DISCO_MID_ALT") ? atoi(getenv("DISCO_MID_ALT")) : 0;
-        if (alt == 1) return launch_cfg<C, K, 2, 3>(a, st);
-        if (alt == 2) return launch_cfg<C, K, 2, 4>(a, st);
-        if (alt == 3) return launch_cfg<C, K, 4, 4>(a, st);
-    }
     return launch_cfg<C, K, KS, NPART>(a, st);
 }
 

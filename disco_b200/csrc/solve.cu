@@ -224,21 +224,31 @@ DISCO_DEV double g_top_eigpair(const cd* A, cd* B, int l, unsigned gm, cd* v_out
         for (int j = 0; j < D; ++j) B[l * P + j] = it * A[l * P + j];
     }
     __syncwarp(gm);
+    // B is Hermitian, so is B^2: lane l computes only the H = D/2 + 1 entries (l, (l + s) mod D), s = 0..D/2, of
+    // its row (every unordered pair has an owner; for even D the pairs at distance D/2 have two owners that
+    // compute and store the same numbers) and stores each with its conjugate mirror: ~half the D^3 complex MACs.
+    constexpr int H = D / 2 + 1;
+    int col[H];
+#pragma unroll
+    for (int s = 0; s < H; ++s) col[s] = (l + s) % D;
     for (int iter = 0; iter < 40; ++iter) {
-        cd c[D];
+        cd c[H];
         double fro = 0.0, dg = 0.0;
         if (act) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) c[j] = mk(0.0, 0.0);
+            for (int s = 0; s < H; ++s) c[s] = mk(0.0, 0.0);
             for (int k = 0; k < D; ++k) {
                 const cd blk = B[l * P + k];
 #pragma unroll
-                for (int j = 0; j < D; ++j) c[j] = c[j] + blk * B[k * P + j];
+                for (int s = 0; s < H; ++s) c[s] = c[s] + blk * B[k * P + col[s]];
             }
+            dg = c[0].x;
+            fro = c[0].x * c[0].x;                  // the diagonal of a Hermitian square is real
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                fro += norm2(c[j]);
-                if (j == l) dg = c[j].x;
+            for (int s = 1; s < H; ++s) {
+                // off-diagonal entries count twice (mirror); for even D the distance-D/2 pairs are owned twice
+                const double wgt = (D % 2 == 0 && s == D / 2) ? 1.0 : 2.0;
+                fro += wgt * norm2(c[s]);
             }
         }
         const double trc = gsum<G>(dg, gm);      // tr(B^2) = ||B||_F^2 of the previous iterate (<= 1)
@@ -246,9 +256,13 @@ DISCO_DEV double g_top_eigpair(const cd* A, cd* B, int l, unsigned gm, cd* v_out
         __syncwarp(gm);                          // everyone has finished reading B
         if (act) {
             const double it = 1.0 / trc;
+            B[l * P + l] = mk(it * c[0].x, 0.0);
 #pragma unroll
-            for (int j = 0; j < D; ++j) B[l * P + j] = it * c[j];
-            B[l * P + l].y = 0.0;
+            for (int s = 1; s < H; ++s) {
+                const cd v = it * c[s];
+                B[l * P + col[s]] = v;
+                B[col[s] * P + l] = conj(v);
+            }
         }
         __syncwarp(gm);
         if (1.0 - fr2 / (trc * trc) <= 1e-14) break;   // new iterate is rank one (group-uniform)
