@@ -28,6 +28,7 @@ struct WideCfg {
     static constexpr size_t SMEM_RED = TW > 1 ? (size_t)NPART * NPP * 2 * 32 * sizeof(float2) : 0;
     static constexpr size_t SMEM = SMEM_PIPE > SMEM_RED ? SMEM_PIPE : SMEM_RED;
     static_assert(TS % TW == 0 && NW % TS == 0, "loader fast path: every thread keeps one slot");
+    static_assert(SL % NPART == 0 || NPART > 2, "fused z output: the slots of a way are dealt to its partitions");
 };
 
 DISCO_DEV const float2* wide_channel(const CatArgs& in, int grp, int d) {
@@ -51,7 +52,9 @@ DISCO_DEV void wide_tile(const ScmArgs& a, const float2* yb, const float* mb, co
         for (int d = 0; d < D; ++d) x[d] = yb[(d * TS + s * TW) * 32];
         const float m = has_mask ? mb[s * TW * 32] : 1.f;
         wide_point<D, NPART, PART>(x, m, has_mask, ps, pn);
-        if constexpr (ZF && PART == 0) {     // K == 1, D == C: z = w1^H y, zn = y[ref] - z  (tango.py:369-376)
+        // K == 1, D == C: z = w1^H y, zn = y[ref] - z (tango.py:369-376); slot s is written by partition s % NPART
+        // (every partition holds all D operands), which balances the extra work over the partitions
+        if (ZF && (s % NPART == PART)) {
             const int t = tfirst + s * TW * lg.tmul;
             float2 z = cmul(w1s[0], x[0]), yr = x[0];
 #pragma unroll
@@ -179,7 +182,7 @@ static cudaError_t launch_wide_dz(const ScmArgs& a, cudaStream_t st) {
     using G = WideCfg<D, NPART, TW, TS, NS>;
     constexpr int THREADS = 32 * G::NW;
     constexpr int BY_SMEM = (int)((227 * 1024) / (G::SMEM + 1024));
-    constexpr int BY_REGS = 65536 / (THREADS * (4 * G::NPP + 3 * D + 28));
+    constexpr int BY_REGS = 65536 / (THREADS * (4 * G::NPP + 3 * D + 26));
     constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
     auto kern = masked_scm_wide_kernel<D, NPART, TW, TS, NS, ZF, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
