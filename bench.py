@@ -349,7 +349,7 @@ def main():
                "roofline": roof}
         if e2e:
             res["e2e"] = e2e
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU leg is an N = 1 measurement (rank 0 owns the whole host)
             res["cpu_baseline"] = cpu_baseline(K, C, L, n_fft, budget_s=12.0)
             res["cpu_baseline_vectorized"] = cpu_baseline(K, C, L, n_fft, budget_s=6.0, granularity="bin")
         print(json.dumps(res))
