@@ -194,6 +194,10 @@ static cudaError_t launch_d(const FilterArgs& a, cudaStream_t st) {
 
 cudaError_t launch_filter_sum(const FilterArgs& a, cudaStream_t st) {
     const int D = a.in.C + a.in.K - 1;
+    {   // all nodes of a multi-node array, frame-major output: one pass over Y and Z (filter_sum_multi.cu)
+        const cudaError_t e = launch_filter_sum_multi(a, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (D) {
         case 1: return launch_d<1>(a, st);
         case 2: return launch_d<2>(a, st);

@@ -82,6 +82,7 @@ struct FilterArgs {
     int out_ft;
 };
 cudaError_t launch_filter_sum(const FilterArgs& a, cudaStream_t st);
+cudaError_t launch_filter_sum_multi(const FilterArgs& a, cudaStream_t st);   // K > 1, all nodes, TF output
 
 // Fused multi-node middle pass (mid_multi.cu): z, zn of every node + step-2 SCMs of every node.
 struct MidArgs {

@@ -319,3 +319,27 @@ def test_wide_scm_paths_long_and_short_sequences(dev, n_fft, T):
         Rs, Rn = tango_f64.masked_scm(X.transpose(0, 2, 1), m[b, k].T)
         assert rel_l2(_np(Rss)[b, k], Rs) < 3e-6 and rel_l2(_np(Rnn)[b, k], Rn) < 3e-6
         assert rel_l2(_np(Rss)[b, k, F - 1], Rs[F - 1]) < 3e-6
+
+
+@pytest.mark.parametrize("C,K,T,n_fft,ref", [(2, 3, 301, 256, 3), (4, 4, 130, 512, 0), (2, 8, 9, 1024, 5), (1, 2, 40, 512, 1)])
+def test_filter_sum_all_nodes_one_pass(dev, C, K, T, n_fft, ref):
+    """The one-pass all-nodes kernel (frame-major output) == the per-node kernel (reached through the (F, T) output
+    layout) == einsum; reference channel on a microphone or on a compressed signal; conj and plain weights."""
+    from disco_b200 import ops
+    rng = np.random.default_rng(C * 100 + K)
+    B, F, D = 2, n_fft // 2 + 1, C + K - 1
+    cplx = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)
+    Y, Z, W = cplx(B, K, C, T, F), cplx(B, K, T, F), cplx(B, K, F, D)
+    Yd, Zd, Wd = (torch.from_numpy(a).to(dev) for a in (Y, Z, W))
+    out, res = ops.filter_sum(Wd, Yd, Zd, conj=True, ref=ref, n_fft=n_fft, out_layout="TF")
+    out2, res2 = ops.filter_sum(Wd, Yd, Zd, conj=True, ref=ref, n_fft=n_fft, out_layout="FT")
+    assert rel_l2(_np(out), _np(out2).transpose(0, 1, 3, 2)) < 1e-6 and rel_l2(_np(res), _np(res2).transpose(0, 1, 3, 2)) < 1e-6
+    for b, k in [(0, 0), (1, K - 1), (1, K // 2)]:
+        X = np.concatenate([Y[b, k], Z[b, [j for j in range(K) if j != k]]], axis=0)       # (D, T, F)
+        want = np.einsum("fd,dtf->tf", W[b, k].conj(), X)
+        assert rel_l2(_np(out)[b, k], want) < 1e-6
+        assert rel_l2(_np(res)[b, k], X[ref] - want) < 2e-6
+        assert rel_l2(_np(out)[b, k, :, F - 1], want[:, F - 1]) < 1e-6                      # the Nyquist bin on its own
+    plain = ops.filter_sum(Wd, Yd, Zd, conj=False, n_fft=n_fft, out_layout="TF")
+    X = np.concatenate([Y[0, 1], Z[0, [j for j in range(K) if j != 1]]], axis=0)
+    assert rel_l2(_np(plain)[0, 1], np.einsum("fd,dtf->tf", W[0, 1], X)) < 1e-6
