@@ -32,7 +32,11 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
     const int b = blockIdx.y, T = a.in.T, F = a.in.F;
     const LaneGeom lg = lane_geom(blockIdx.x, lane, F);
     const int tspan = TS * lg.tmul;
-    const int ntile = (T + tspan - 1) / tspan;
+    const int ntile_all = (T + tspan - 1) / tspan;
+    // the outputs of different frames are independent: gridDim.z CTAs split the tiles of a (utterance, bin block)
+    const int tile0 = (int)((long long)ntile_all * blockIdx.z / gridDim.z);
+    const int ntile = (int)((long long)ntile_all * (blockIdx.z + 1) / gridDim.z) - tile0;
+    if (ntile <= 0) return;
 
     for (int i = warp; i < K * D; i += NW) {           // filters of every node for this lane's bin
         const float2 v = a.W[((size_t)(b * K + i / D) * F + lg.fcol) * D + i % D];
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
     const int lslot = warp % TS;                       // NW % TS == 0: a thread always loads the same slot
     auto issue = [&](int i) {
         if (i < ntile) {
-            const int t = i * tspan + lg.tl + lslot * lg.tmul;
+            const int t = (tile0 + i) * tspan + lg.tl + lslot * lg.tmul;
             const bool v = lg.ok && t < T;
             const size_t toff = (size_t)(v ? t : 0) * F;
             float2* dst = stage + ((i % NS) * G::ROWS + warp) * 32 + lane;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
                     acc = cadd(acc, cmul(wk[(C + r) * 32], x));
                     if (C + r == a.ref) xr = x;
                 }
-                const int t = i * tspan + lg.tl + ts * lg.tmul;
+                const int t = (tile0 + i) * tspan + lg.tl + ts * lg.tmul;
                 if (lg.ok && t < T) {
                     const size_t o = ((size_t)(b * K + k) * T + t) * F + lg.fcol;
                     a.out[o] = acc;
@@ -107,7 +111,14 @@ static cudaError_t launch_fsm(const FilterArgs& a, cudaStream_t st) {
     auto kern = filter_sum_multi_kernel<C, K, NS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) return e;
-    dim3 grid((a.in.F + 31) / 32, a.in.n_grp / K);
+    // enough CTAs for ~8 waves of the resident slots (equal-sized CTAs: few waves quantise badly), at least 8 tiles each
+    const int nblk = (a.in.F + 31) / 32, B = a.in.n_grp / K;
+    const int by_smem = (int)((227 * 1024) / (G::SMEM + 1024));
+    const int slots = 148 * (by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem));
+    int nseg = (8 * slots + nblk * B - 1) / (nblk * B);
+    const int max_seg = (a.in.T / G::TS + 7) / 8;
+    nseg = nseg < 1 ? 1 : (nseg > max_seg ? (max_seg < 1 ? 1 : max_seg) : nseg);
+    dim3 grid(nblk, B, nseg);
     kern<<<grid, 256, G::SMEM, st>>>(a);
     return cudaGetLastError();
 }
