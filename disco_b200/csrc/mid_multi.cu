@@ -11,7 +11,7 @@
 //   loads    all K*C microphone spectra and the KS masks of tile i+NS-1 -> stage ring (asynchronous)
 //   phase A  z_j of ALL K nodes for tile i+1 from shared memory -> double-buffered z tile (+ z, zn
 //            written out once); items (node, frame) dealt round-robin to the warps
-//   phase B  warp (node k, pair-partition p[, time-way]) accumulates its share of the D(D+1)/2 Hermitian
+//   phase B  warp (node k, pair-partition p) accumulates its share of the D(D+1)/2 Hermitian
 //            pairs of tile i in registers: own C spectra and the other nodes' z from shared memory
 // with ONE barrier per tile (phase A runs one tile ahead of phase B).  The SCMs are written directly.
 // Channels are accumulated in ROTATED node order (own mics, then z_{k+1}, z_{k+2}, ... mod K) so that all

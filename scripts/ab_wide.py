@@ -1,5 +1,5 @@
-"""Per-op CUDA-event timing of the wide-channel kernels on BASELINE shapes.  AB_ONLY=<name> restricts the shapes,
-DISCO_MID_ALT=<n> selects an alternative CTA shape of the fused middle pass (experiments).  Prints microseconds."""
+"""Per-op CUDA-event timing of the wide-channel kernels on BASELINE shapes (AB_ONLY=<name> restricts the shapes).
+Prints microseconds per launch (median of 20 after 3 warm-up launches)."""
 import os
 import sys
 
@@ -28,7 +28,7 @@ def main():
     T, F = 626, 257
     gen = torch.Generator(device=dev).manual_seed(1)
     cplx = lambda *s: torch.view_as_complex(torch.randn(*s, 2, device=dev, generator=gen))
-    tag = "alt" + os.environ.get("DISCO_MID_ALT", "0")
+    tag = "r1"
     only = os.environ.get("AB_ONLY")
     for name, B, K, C in [("cfg3", 64, 4, 4), ("cfg5", 64, 8, 2), ("cfg4", 128, 1, 8), ("k2c4", 64, 2, 4)]:
         if only and name != only:
