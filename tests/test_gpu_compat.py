@@ -1,4 +1,6 @@
 """Reference-signature adapters (disco_b200/compat) on the GPU against the reference's outputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -89,3 +91,26 @@ def test_get_z_signals_step1_twin():
             ref = g["%s_%d" % (nm, k)]
             assert np.linalg.norm(np.abs(got[k]) - np.abs(ref)) / np.linalg.norm(np.abs(ref)) < 1e-5
         assert np.max(np.abs(mz[k] - g["masks_z_%d" % k])) < 5e-6
+
+
+def test_metrics_reference_signatures():
+    """compat.metrics: the reference's call signatures (one 1-D NumPy signal per call) against its own outputs."""
+    from disco_b200.compat import metrics as m
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_kat.npz"))
+    fs = int(g["fs"])
+    s, n, est, vad = g["s"], g["n"], g["est"], g["vad"]
+    for i in range(3):
+        fq, mean, F = m.fw_snr(s[i], n[i], fs)
+        assert isinstance(mean, float) and fq.shape == (17,) and np.array_equal(F, g["F"])
+        assert abs(mean - g["fw_snr_mean_%d" % i]) < 1e-6 and np.max(np.abs(fq - g["fw_snr_fq_%d" % i])) < 1e-6
+        _, mean_v, _ = m.fw_snr(s[i], n[i], fs, vad_tar=vad[i], vad_noi=vad[i])
+        assert abs(mean_v - g["fw_snr_vad_mean_%d" % i]) < 1e-6
+        _, mean_d, _ = m.fw_sd(est[i], s[i], fs)
+        assert abs(mean_d - g["fw_sd_mean_%d" % i]) < 1e-6
+        assert abs(m.snr(s[i], n[i]) - g["snr_%d" % i]) < 1e-4 and abs(m.sd(est[i], s[i]) - g["sd_%d" % i]) < 1e-4
+        assert abs(m.delta_snr(0.8 * s[i], 0.3 * n[i], s[i], n[i]) - g["delta_snr_%d" % i]) < 1e-4
+        assert abs(m.si_sdr(s[i].astype(np.float64), est[i].astype(np.float64)) - g["si_sdr_%d" % i]) < 1e-6
+    both = m.si_sdr(s[:2].astype(np.float64), est[:2].astype(np.float64))
+    assert both.shape == (2,) and abs(both[1] - g["si_sdr_1"]) < 1e-6
+    with pytest.raises(NotImplementedError):
+        m.fw_snr(np.zeros((10, 2)), np.zeros((10, 2)), fs)
