@@ -58,3 +58,27 @@ def test_wav_codec_roundtrip(tmp_path):
     wav_io.write(p, stereo, 8000)
     y2, fs2 = wav_io.read(p, dtype="float64")
     assert fs2 == 8000 and y2.shape == (8, 2) and np.array_equal(y2[:, 1], -y2[:, 0])
+
+
+def test_post_generator_host_logic(tmp_path):
+    """The host side of dataset_post.PostGenerator (no CUDA needed): data-set split, directory names, channel file
+    ordering (numeric, Ch-10 after Ch-9) and the reference's assertions (post_generator.py:57-97)."""
+    import pytest
+    from disco_b200.dataset_post import PostGenerator
+    from oracle.make_golden import make_post_dataset
+    root = str(tmp_path)
+    make_post_dataset(root, rirs=(1,), lengths=(2000,))
+    gen = PostGenerator(1, 1, "living", "fs", [0, 6], root, n_samples=[10, 2, 2], device="cpu")
+    assert gen.case == "train" and gen.snr_dir == "0-6" and gen.n_ch == 16
+    tar, noi = gen.get_sig_lists(1)
+    assert len(tar) == 16 and len(noi) == 1 and len(noi[0]) == 16
+    assert [int(p.split("_Ch-")[-1].split(".wav")[0]) for p in tar] == list(range(1, 17))
+    tars, nois = gen.load_sigs(tar, noi)
+    assert tars.shape == (16, 2000) and nois.shape == (16, 2000) and tars.dtype == np.float32
+    assert PostGenerator(11, 1, "living", "fs", [0, 6], root, n_samples=[10, 4, 2], device="cpu").case == "val"
+    with pytest.raises(AssertionError):
+        PostGenerator(9, 3, "living", "fs", [0, 6], root, n_samples=[10, 2, 2], device="cpu")      # spans two sets
+    with pytest.raises(AssertionError):
+        PostGenerator(0, 1, "living", "fs", [0, 6], root, n_samples=[10, 2, 2], device="cpu")
+    with pytest.raises(ValueError):
+        PostGenerator(1, 1, "living", "fs", [0, 6], root, n_fft=512, n_hop=128, n_samples=[10, 2, 2], device="cpu")
