@@ -32,7 +32,9 @@ def online_mwf(Y, mask, Z=None, lambda_cor=0.95, block=8, lag=1, mu=1.0, filter_
 def online_tango(y, masks, lambda_cor=0.95, block=8, lag=1, mu=1.0, rank=1, ref_mic=0, n_fft=512, R0=None):
     """Two-step recursive Tango on time signals y [B, K, C, L]: local recursive MWF -> exchange of the compressed
     signals z -> recursive MWF on [own mics ; z of the other nodes] (the channel order of concatenate_signals,
-    tango.py:142-155).  masks = (mask_z, mask_w) [B, K, T, F] frame-major.  Returns yf, z_y, zn [B, K, T, F]."""
+    tango.py:142-155).  masks = (mask_z, mask_w) [B, K, T, F] frame-major; R0 = optional initial (R_ss, R_nn) of the
+    local step [B, K, F, C, C] (the second step of a multi-node array starts from zeros).  Returns yf, z_y, zn
+    [B, K, T, F] and the per-block filters W1, W2."""
     mask_z, mask_w = masks
     mask_w = mask_z if mask_w is None else mask_w
     Y = ops.stft(y, n_fft)
