@@ -2,19 +2,25 @@
 """Benchmark of the B200 MWF beamforming hot path (BASELINE.json metric: beamformed frames/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|...]
+                    [--shard utterances|nodes] [--masks oracle|crnn]
 
 One "step" = one pass of the whole two-step Tango path (STFT -> masked SCM -> per-bin GEVD-MWF
--> filter-and-sum, twice) over one batch of synthetic utterances.  Default workload = BASELINE
-configs[1]: 1 node x 4 mics, batch = 64 x 10 s @ 16 kHz per GPU, 512-pt STFT, device-resident
-DNN-style masks.  Frame unit: one STFT frame of one node's beamformed output, so a
-step produces B*K*T frames per GPU.  N > 1: utterances shard over ranks, no data-path collective
-(weak scaling); timing = max over ranks of CUDA-event time between barriers.
+-> filter-and-sum, twice) over one batch of synthetic utterances, in DEPLOYMENT mode: the mixture y
+and the two masks are the inputs, yf / z / zn the outputs (no clean components, no diagnostics) --
+the same work in the GPU arm and in the CPU arm.  Default workload = BASELINE configs[1]: 1 node x
+4 mics, batch = 64 x 10 s @ 16 kHz per GPU, 512-pt STFT, device-resident masks.  Frame unit
+(SURVEY.md 8d): one STFT frame of one node's beamformed output, so a step produces B*K*T frames per
+GPU.  N > 1: utterances shard over ranks, no data-path collective (weak scaling); --shard nodes
+instead gives every rank K/N nodes of every utterance and exchanges the compressed signals z with
+one NCCL all-gather per batch chunk (reference tango.py:379-386), overlapped with step 1 of the next
+chunk.  Timing = max over ranks of CUDA-event time between barriers.
 
 The JSON line also carries
-  roofline      the fused stft_scm kernel: algorithmic bytes (SURVEY.md 8d:
-                4CL + 4FT + 8CFT + 16FC^2 per group) / its CUDA-event time, vs the measured HBM peak
+  roofline      the dominant kernel of the step (algorithmic bytes / CUDA-event time vs the measured
+                HBM peak) and, under "kernels", the same for EVERY kernel of the step
   e2e           the same metric through the public API with pinned HOST buffers (H2D of signals and
-                masks, D2H of the beamformed STFT inside the timed region)
+                masks, D2H of the beamformed STFT inside the timed region); --masks crnn: only the
+                signals cross PCIe (int16 PCM), the masks come from the reference's CRNN on device
   cpu_baseline  the oracle port of the reference (oracle/tango_np.py, per-frame np.outer loops
                 like tango.py:357-374) on the host cores, bounded sample
 --impl reference times only that CPU path (the reference is pure Python/NumPy and cannot travel to
@@ -38,30 +44,33 @@ WORKLOADS = {
     # name: (B per GPU, K nodes, C mics, L samples, n_fft, description)
     "cfg1": (1, 1, 2, 64000, 512, "1 node x 2 mics, 4 s, 512-pt STFT (BASELINE configs[0])"),
     "cfg2": (64, 1, 4, 160000, 512, "1 node x 4 mics, batch=64 x 10 s per GPU, 512-pt STFT, DNN mask (BASELINE configs[1])"),
-    "cfg3": (64, 4, 4, 160000, 512, "4 nodes x 4 mics, batch=64 x 10 s per GPU, all nodes on-GPU (BASELINE configs[2] shape)"),
+    "cfg3": (64, 4, 4, 160000, 512, "4 nodes x 4 mics, batch=64 x 10 s per GPU (BASELINE configs[2] shape)"),
     "cfg5": (64, 8, 2, 160000, 512, "8 nodes x 2 mics, batch=64 x 10 s per GPU (BASELINE configs[4] shape)"),
     "cfg4_256": (128, 1, 8, 160000, 256, "8 mics, 256-pt STFT, batch=128 x 10 s per GPU (BASELINE configs[3] sweep point)"),
     "cfg4_512": (128, 1, 8, 160000, 512, "8 mics, 512-pt STFT, batch=128 x 10 s per GPU (BASELINE configs[3] sweep point)"),
     "cfg4_1024": (128, 1, 8, 160000, 1024, "8 mics, 1024-pt STFT, batch=128 x 10 s per GPU (BASELINE configs[3] sweep point)"),
 }
-
-
-def stft_scm_bytes(C, L, n_fft):
-    F, T = n_fft // 2 + 1, 1 + L // (n_fft // 2)
-    return 4 * C * L + 4 * F * T + 8 * C * F * T + 16 * F * C * C
+METRIC = "beamformed frames/sec (16kHz, 512-pt STFT)"
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference), bounded sample, one utterance per process
+# CPU arm: the oracle port of the reference in deployment mode (masks given), bounded sample,
+# one utterance per host process (exp/ex1/loop_tango.sh launches one process per utterance)
 # ----------------------------------------------------------------------------------------------
 def _cpu_one(args):
     seed, K, C, L, n_fft, gran = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from disco_b200.synth import make_utterance
-    from oracle import tango_np
+    from oracle import librosa_np, tango_np
     y, s, n = make_utterance(seed, K, C, L)
+    hop = n_fft // 2
+    # masks are an INPUT of the timed path (they come from the DNN in deployment): computed outside the clock
+    S = [librosa_np.stft(s[k, 0], n_fft, hop) for k in range(K)]
+    N = [librosa_np.stft(n[k, 0], n_fft, hop) for k in range(K)]
+    mz = [tango_np.tf_mask(S[k], N[k], "irm1") for k in range(K)]
+    mw = [tango_np.tf_mask(S[k], N[k], "irm2") for k in range(K)]
     t0 = time.perf_counter()
-    tango_np.offline_tango(list(y), list(s), list(n), n_fft=n_fft, n_hop=n_fft // 2, granularity=gran)
+    tango_np.offline_tango(list(y), None, None, masks=(mz, mw), n_fft=n_fft, n_hop=hop, granularity=gran)
     return time.perf_counter() - t0
 
 
@@ -89,30 +98,41 @@ def usable_cores():
     return max(1, min(n, 64))
 
 
-def cpu_baseline(K, C, L, n_fft, budget_s=20.0, granularity="frame", procs=None):
-    """frames/s of the oracle port with one utterance per host process (how the reference
-    parallelises: exp/ex1/loop_tango.sh launches one process per utterance)."""
-    import multiprocessing as mp
-    cores = procs or usable_cores()
-    T = 1 + L // (n_fft // 2)
-    # bound the sample: shorten the utterance so one of them takes <~ budget (the reference runs ~120 frames/s/core)
-    est_rate = 110.0 if granularity == "frame" else 20000.0
-    max_frames = max(64, int(budget_s * est_rate / K))
-    Ls = min(L, (max_frames - 1) * (n_fft // 2))
-    Ts = 1 + Ls // (n_fft // 2)
-    ctx = mp.get_context("spawn")
-    os.environ["OMP_NUM_THREADS"] = "1"          # inherited by the workers: one thread per process
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["MKL_NUM_THREADS"] = "1"
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_warm, range(cores), chunksize=1)          # interpreter + NumPy/SciPy imports: untimed
+class CpuArm:
+    """Pool of host processes (started and warmed once); sample() times one bounded sample."""
+
+    def __init__(self, K, C, L, n_fft, procs=None):
+        import multiprocessing as mp
+        self.K, self.C, self.L, self.n_fft = K, C, L, n_fft
+        self.cores = procs or usable_cores()
+        os.environ["OMP_NUM_THREADS"] = "1"          # inherited by the workers: one thread per process
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        os.environ["MKL_NUM_THREADS"] = "1"
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_cpu_warm, range(self.cores), chunksize=1)      # interpreter + NumPy/SciPy imports: untimed
+        self.seed = 1000
+
+    def sample(self, budget_s, granularity="frame"):
+        K, C, L, n_fft = self.K, self.C, self.L, self.n_fft
+        # bound the sample: shorten the utterance so one of them takes <~ budget (the reference runs ~120 frames/s/core)
+        est_rate = 150.0 if granularity == "frame" else 20000.0
+        max_frames = max(64, int(budget_s * est_rate / K))
+        Ls = min(L, (max_frames - 1) * (n_fft // 2))
+        Ts = 1 + Ls // (n_fft // 2)
+        jobs = [(self.seed + i, K, C, Ls, n_fft, granularity) for i in range(self.cores)]
+        self.seed += self.cores
         t0 = time.perf_counter()
-        pool.map(_cpu_one, [(1000 + i, K, C, Ls, n_fft, granularity) for i in range(cores)], chunksize=1)
+        self.pool.map(_cpu_one, jobs, chunksize=1)
         wall = time.perf_counter() - t0
-    return {"value": cores * K * Ts / wall, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "%d utterances (one per process) x %d node(s) x %d mics x %.2f s (%d frames), oracle/tango_np.py "
-                      "granularity=%s, workers pre-started" % (cores, K, C, Ls / 16000.0, Ts, granularity),
-            "seconds": wall, "frames": cores * K * Ts}
+        return {"value": self.cores * K * Ts / wall, "unit": "frames/s", "cores": self.cores, "kind": "port",
+                "sample": "%d utterances (one per process) x %d node(s) x %d mics x %.2f s (%d frames), oracle/tango_np.py "
+                          "deployment mode (masks given; yf, z, zn), granularity=%s, workers pre-started"
+                          % (self.cores, K, C, Ls / 16000.0, Ts, granularity),
+                "seconds": wall, "frames": self.cores * K * Ts}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -160,6 +180,141 @@ def summarize_clocks(samples):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------------------------
+# Per-kernel accounting: algorithmic bytes of every op of the step, from the
+# shapes of the tensors it is called with
+# ----------------------------------------------------------------------------------------------
+def _op_models(n_fft):
+    F = n_fft // 2 + 1
+
+    def dims(Y):
+        C, T = Y.shape[-3], Y.shape[-2]
+        return Y.numel() // (C * T * F), C, T          # groups, channels, frames
+
+    def stft_scm(a, k, nm):
+        x = a[0]
+        G, C, L = x.shape
+        T = 1 + L // (n_fft // 2)
+        keep = k.get("keep_partials", False) or nm == 2
+        return ("stft_scm_kernel<%d,%d,%d>" % (n_fft, C, nm),
+                G * (4 * C * L + nm * 4 * F * T + 8 * C * F * T + nm * 16 * F * C * C), 1 if keep else 2)
+
+    def solve(n_mat, D):
+        return n_mat * (16 * D * D + 16 * D)
+
+    def filter_sum(a, k):
+        W, Y = a[0], a[1]
+        Z = a[2] if len(a) > 2 else k.get("Z")
+        G, C, T = dims(Y)
+        D = W.shape[-1]
+        resid = k.get("ref") is not None
+        if Z is not None and k.get("out_layout", "TF") in ("TF", 0) and k.get("node_sel") is None:
+            Kn = Z.shape[1]   # all-nodes pass: Y and every z read once
+            return ("filter_sum_multi_kernel<%d,%d>" % (C, Kn), (G // Kn) * (8 * Kn * C * F * T + 16 * Kn * F * T + 8 * Kn * F * D), 1)
+        return ("filter_sum<%d>" % D, G * (8 * D * F * T + 8 * F * D + (16 if resid else 8) * F * T), 1)
+
+    def masked_scm(a, k):
+        Y = a[0]
+        Z = a[2] if len(a) > 2 else k.get("Z")
+        G, C, T = dims(Y)
+        D = C + (Z.shape[1] - 1 if Z is not None else 0)
+        return ("masked_scm<%d>" % D, G * (8 * D * F * T + 4 * F * T + 16 * F * D * D), 1)
+
+    def filter_sum_scm(a, k):
+        G, C, T = dims(a[1])
+        return ("masked_scm<%d,ZF>" % C, G * (8 * C * F * T + 4 * F * T + 16 * F * T + 16 * F * C * C), 1)
+
+    def tango_mid(a, k):
+        Y = a[1]
+        B, Kn, C, T, _ = Y.shape
+        D = C + Kn - 1
+        return ("tango_mid_kernel<%d,%d>" % (C, Kn), B * (8 * Kn * C * F * T + 4 * Kn * F * T + 16 * Kn * F * T + 16 * Kn * F * D * D), 1)
+
+    def filter_dual(a, k):
+        G, C, T = dims(a[2])
+        return ("filter_dual_kernel<%d>" % C, G * (8 * C * F * T + 24 * F * T + 16 * F * C), 1)
+
+    def stft(a, k):
+        x = a[0]
+        L = x.shape[-1]
+        n = x.numel() // L
+        return ("stft_scm_kernel<%d,*,0>" % n_fft, n * (4 * L + 8 * F * (1 + L // (n_fft // 2))), 1)
+
+    return {
+        "stft": stft,
+        "stft_scm": lambda a, k: stft_scm(a, k, 1),
+        "stft_scm2": lambda a, k: stft_scm(a, k, 2),
+        "mwf_solve_workspace": lambda a, k: ("mwf_solve_kernel<%d,partials>" % a[2], solve(a[1] * F, a[2]), 1),
+        "mwf_solve_workspace2": lambda a, k: ("mwf_solve_kernel<%d,partials,2 sets>" % a[2], solve(2 * a[1] * F, a[2]), 1),
+        "mwf_solve": lambda a, k: ("mwf_solve_kernel<%d>" % a[0].shape[-1], solve(a[0].numel() // a[0].shape[-1] ** 2, a[0].shape[-1]), 1),
+        "filter_sum": filter_sum,
+        "masked_scm": masked_scm,
+        "filter_sum_scm": filter_sum_scm,
+        "tango_mid": tango_mid,
+        "filter_dual": filter_dual,
+    }
+
+
+class KernelTimer:
+    """Wraps the ops the pipeline calls with CUDA events on their launch stream (eager steps only)."""
+
+    def __init__(self, ops_mod, n_fft):
+        import torch
+        self.torch, self.ops = torch, ops_mod
+        self.models = _op_models(n_fft)
+        self.orig = {}
+        self.calls = []          # (key, name, bytes, launches, ev0, ev1) of the CURRENT step
+        self.steps = []
+        self.on = False
+
+    def __enter__(self):
+        for name, model in self.models.items():
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+            setattr(self.ops, name, self._wrap(name, fn, model))
+        return self
+
+    def _wrap(self, name, fn, model):
+        def timed(*a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            label, nbytes, launches = model(a, k)
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.calls.append(("%d:%s" % (len(self.calls), name), label, nbytes, launches, e0, e1))
+            return r
+        return timed
+
+    def step(self, fn):
+        self.on, self.calls = True, []
+        fn()
+        self.on = False
+        self.steps.append(self.calls)
+
+    def __exit__(self, *exc):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+
+    def summary(self, peak_gbs):
+        self.torch.cuda.synchronize()
+        rows = {}
+        for calls in self.steps:
+            for key, label, nbytes, launches, e0, e1 in calls:
+                r = rows.setdefault(key, {"kernel": label, "bytes": nbytes, "launches": launches, "ms": []})
+                r["ms"].append(e0.elapsed_time(e1))
+        out = []
+        for key in sorted(rows, key=lambda k: int(k.split(":")[0])):
+            r = rows[key]
+            ms = float(np.mean(r["ms"]))
+            gbs = r["bytes"] / (ms / 1e3) / 1e9
+            out.append({"op": key.split(":")[1], "kernel": r["kernel"], "launches": r["launches"], "us": 1e3 * ms,
+                        "algorithmic_bytes": int(r["bytes"]), "achieved_gbs": gbs, "frac": gbs / peak_gbs})
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,7 +326,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="batch slices of the host-to-host pipeline")
-    ap.add_argument("--chunks", type=int, default=1, help="batch chunks captured on parallel graph branches")
+    ap.add_argument("--chunks", type=int, default=0, help="batch chunks captured on parallel graph branches (0 = auto)")
+    ap.add_argument("--shard", default="utterances", choices=["utterances", "nodes"])
+    ap.add_argument("--masks", default="oracle", choices=["oracle", "crnn"],
+                    help="e2e leg: masks uploaded from the host (oracle) or predicted on device by the reference CRNN")
     args = ap.parse_args()
     B, K, C, L, n_fft, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -180,25 +338,41 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.shard == "nodes":
+        from bench_nodes import main_nodes          # node-sharded distributed MWF (all-gather of z)
+        return main_nodes(args, WORKLOADS, METRIC, summarize_clocks, clock_sampler)
+    chunks = args.chunks if args.chunks > 0 else (2 if K > 1 else 1)
+    chunks = max(1, min(chunks, B))
     config = {"workload": "%s: %s" % (args.workload, desc), "nodes": K, "mics_per_node": C, "utterance_s": L / 16000.0,
               "n_fft": n_fft, "hop": n_fft // 2, "batch_per_gpu": B, "global_batch": B * world, "frames_per_step": B * K * T * world,
-              "mask": "device-resident synthetic DNN-style masks U[0,1], frame-major (T,F)", "parallelism": "utterance-sharded x%d, no collective" % world, "execution": "CUDA graph, %d batch chunk(s) on parallel branches" % max(1, min(args.chunks, B)),
+              "mode": "deployment: inputs = mixture y + masks (mask_z, mask_w), outputs = yf, z, zn; same work in the CPU arm",
+              "inputs": "%d distinct synthetic utterances per GPU (coherent source + white noise, disco_b200/synth.py)" % B,
+              "mask": "device-resident masks, frame-major (T,F): mask_z = irm1, mask_w = irm2 of the clean components' "
+                      "reference channel (tf_mask, dnn/utils.py:44-71)",
+              "parallelism": "utterance-sharded x%d, no collective" % world,
+              "execution": "CUDA graph, %d batch chunk(s) on parallel branches" % chunks,
               "l2": "inputs larger than L2 (y %.0f MB, Y %.0f MB per GPU)" % (B * K * C * L * 4 / 1e6, B * K * C * T * F * 8 / 1e6)}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        t_all, frames = 0.0, 0
-        last = None
-        for i in range(max(1, min(args.steps, 3))):          # each step = one bounded sample on all host cores
-            last = cpu_baseline(K, C, L, n_fft, budget_s=15.0)
+        arm = CpuArm(K, C, L, n_fft)
+        steps = max(1, args.steps)
+        budget = max(2.0, min(15.0, 150.0 / (steps + min(args.warmup, 1))))     # whole run within a few minutes
+        if args.warmup > 0:
+            arm.sample(min(budget, 3.0))                                       # one untimed warm-up sample
+        t_all, frames, last = 0.0, 0, None
+        for _ in range(steps):            # each step = one bounded sample on all host cores
+            last = arm.sample(budget)
             t_all += last["seconds"]
             frames += last["frames"]
+        arm.close()
         val = frames / t_all
-        last["value"] = val
-        print(json.dumps({"impl": "reference", "metric": "beamformed frames/sec (16kHz, 512-pt STFT)", "value": val,
-                          "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * t_all / max(1, min(args.steps, 3)), "higher_is_better": True, "scaling": "weak",
+        last = dict(last, value=val, seconds=t_all, frames=frames,
+                    sample=last["sample"] + "; %d such samples" % steps)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val,
+                          "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+                          "ms_per_step": 1e3 * t_all / steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "c64 SCM/cggev, c128 filters (reference dtype flow)", "data": "synthetic",
                           "config": config, "cpu_baseline": last,
                           "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -214,20 +388,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- synthetic inputs (seeded): a few distinct utterances tiled to the batch, masks U[0,1]
+    # ---- synthetic inputs (seeded): B distinct utterances; masks from the clean components on the device
     from disco_b200.synth import make_utterance
-    base = [make_utterance(1000 * rank + i, K, C, L)[0] for i in range(4)]
-    y_host = torch.from_numpy(np.stack([base[i % 4] for i in range(B)])).pin_memory()      # [B,K,C,L]
-    g = torch.Generator().manual_seed(1234 + rank)
-    mz_host = torch.rand((B, K, T, F), generator=g, dtype=torch.float32).pin_memory()
-    mw_host = torch.rand((B, K, T, F), generator=g, dtype=torch.float32).pin_memory()
-    y, mz, mw = y_host.to(dev), mz_host.to(dev), mw_host.to(dev)
     ops.init(n_fft)
+    y_host = torch.empty((B, K, C, L), dtype=torch.float32).pin_memory()
+    mz = torch.empty((B, K, T, F), dtype=torch.float32, device=dev)
+    mw = torch.empty_like(mz)
+    for b in range(B):
+        yb, sb, nb = make_utterance(100000 * rank + b, K, C, L)
+        y_host[b] = torch.from_numpy(yb)
+        S = ops.stft(torch.from_numpy(np.ascontiguousarray(sb[:, 0])).to(dev), n_fft)
+        N = ops.stft(torch.from_numpy(np.ascontiguousarray(nb[:, 0])).to(dev), n_fft)
+        mz[b], mw[b] = ops.tf_mask(S, N, "irm1"), ops.tf_mask(S, N, "irm2")
+    mz_host, mw_host = mz.cpu().pin_memory(), mw.cpu().pin_memory()
+    y = y_host.to(dev)
     from disco_b200.plan import TangoGraph
-    chunks = max(1, min(args.chunks, B))
-    # stft_scm, mwf_solve, fused middle pass (or filter_sum + masked_scm), mwf_solve, filter_sum
-    kernels_per_chunk = 5 if (K == 1 or ops.tango_mid_supported(C, K)) else 6
-    launches_per_step = kernels_per_chunk * chunks
     plan = TangoGraph(B, K, C, L, n_fft=n_fft, chunks=chunks, device=dev)   # CUDA graph of the whole step
     plan.load(y, mz, mw)
 
@@ -237,7 +412,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed region 1: whole-path throughput, inputs resident in HBM (graph replays)
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):
         plan.run()
     barrier()
     samples, stop = [], threading.Event()
@@ -259,48 +434,41 @@ def main():
     frames = B * K * T * world * args.steps
     value = frames / (ms / 1e3)
 
-    # ---- timed region 2: the fused stft_scm op alone, CUDA events on its launch stream inside eager steps
+    # ---- timed region 2: every kernel of the step, CUDA events on the launch stream inside eager steps
     import disco_b200.tango as tango_mod
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    cur = {"i": -1}
-    orig = ops.stft_scm
-
-    def timed_stft_scm(*a, **k):
-        i = cur["i"]
-        if i < 0:
-            return orig(*a, **k)
-        ev[i][0].record()
-        r = orig(*a, **k)
-        ev[i][1].record()
-        return r
-    tango_mod.ops.stft_scm = timed_stft_scm
 
     def eager_step():
         return tango_batched(y, masks=(mz, mw), n_fft=n_fft, out_layout="TF", diagnostics=False)
     for _ in range(3):
         eager_step()
     barrier()
-    n_k = min(args.steps, 50)
-    for i in range(n_k):
-        cur["i"] = i
-        eager_step()
-    barrier()
-    cur["i"] = -1
-    tango_mod.ops.stft_scm = orig
-    fused = C <= 4          # larger nodes run stft + masked_scm (the fused kernel holds C <= 4)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev[:n_k]])) if fused else None
+    n_k = min(args.steps, 30)
+    with KernelTimer(tango_mod.ops, n_fft) as kt:
+        for i in range(n_k):
+            kt.step(eager_step)
+        barrier()
 
-    # ---- e2e: pinned host buffers in, beamformed STFT out, through the public API (plan.load/run/store)
+    # ---- e2e: pinned host buffers in, beamformed STFT out, through the public API
     e2e = None
     if not args.no_e2e:
         yf_host = torch.empty((B, K, T, F), dtype=torch.complex64).pin_memory()
+        if args.masks == "crnn" and K == 1:
+            from bench_e2e_crnn import CrnnPipeline
+            pipe = CrnnPipeline(B, C, L, n_fft, args.e2e_chunks, dev)
+            y_i16 = pipe.to_pcm(y_host)
 
-        from disco_b200.plan import TangoPipeline
-        pipe = TangoPipeline(B, K, C, L, n_fft=n_fft, chunks=args.e2e_chunks, device=dev)
+            def e2e_step():   # int16 PCM H2D -> CRNN masks on device -> the whole path -> D2H of yf
+                pipe.process(y_i16, yf_host)
+            h2d, how = int(y_i16.numel() * 2), pipe.how
+        else:
+            from disco_b200.plan import TangoPipeline
+            pipe = TangoPipeline(B, K, C, L, n_fft=n_fft, chunks=args.e2e_chunks, device=dev)
 
-        def e2e_step():       # H2D of signals + masks, the whole path, D2H of yf -- overlapped across batch slices
-            pipe.process(y_host, mz_host, mw_host, yf_host)
-        for _ in range(2):
+            def e2e_step():   # H2D of signals + masks, the whole path, D2H of yf -- overlapped across batch slices
+                pipe.process(y_host, mz_host, mw_host, yf_host)
+            h2d = int(y_host.numel() * 4 + 2 * mz_host.numel() * 4)
+            how = "TangoPipeline: %d batch slices, per-slice H2D -> graph replay -> D2H on its own stream (pinned host buffers)" % args.e2e_chunks
+        for _ in range(3):
             e2e_step()
         barrier()
         n_e2e = max(3, min(args.steps // 4, 50))
@@ -313,9 +481,9 @@ def main():
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": B * K * T * world * n_e2e / (float(t2.item()) / 1e3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(y_host.numel() * 4 + 2 * mz_host.numel() * 4),
-               "d2h_bytes_per_step": int(yf_host.numel() * 8), "steps": n_e2e,
-               "how": "TangoPipeline: %d batch slices, per-slice H2D -> graph replay -> D2H on its own stream (pinned host buffers)" % args.e2e_chunks}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(yf_host.numel() * 8), "steps": n_e2e, "how": how}
+        if args.masks == "crnn" and K == 1:
+            e2e["crnn"] = pipe.report()
     stop.set()
 
     if rank == 0:
@@ -325,33 +493,40 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg = stft_scm_bytes(C, L, n_fft) * B * K
-        traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of the kernel, from the committed ncu capture
+        kernels = kt.summary(peak)
+        step_us = sum(k["us"] for k in kernels)
+        for k in kernels:
+            k["share_of_step"] = k["us"] / step_us
+        dom = max(kernels, key=lambda k: k["us"])
+        traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed ncu capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if tj.get("workload") == args.workload and tj.get("batch") == B:
-                traffic = tj["dram_bytes_per_launch"]
+            ent = tj.get(args.workload, {})
+            if ent.get("batch") == B and ent.get("kernel") == dom["kernel"]:
+                traffic = ent["dram_bytes_per_launch"]
         except Exception:
             pass
-        if kern_ms is None:
-            roof = {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                    "note": "C > 4: stft and masked_scm run as two kernels; no fused-kernel roofline for this workload"}
-        else:
-          achieved = alg / (kern_ms / 1e3) / 1e9
-          roof = {"bound": "hbm", "kernel": "stft_scm_kernel<%d,%d,true>" % (n_fft, C), "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / args.steps),
-                "timed": "CUDA events around the op in %d eager steps (the throughput region replays a CUDA graph)" % n_k}
-        res = {"metric": "beamformed frames/sec (16kHz, 512-pt STFT)", "value": value, "unit": "frames/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "kernel_ms": dom["us"] / 1e3,
+                "share_of_step": dom["share_of_step"],
+                "timed": "CUDA events around every op in %d eager steps (the throughput region replays a CUDA graph)" % n_k,
+                "step_algorithmic_bytes": int(sum(k["algorithmic_bytes"] for k in kernels)),
+                "step_frac": sum(k["algorithmic_bytes"] for k in kernels) / (ms / args.steps / 1e3) / 1e9 / peak,
+                "kernels": kernels}
+        res = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (c64 spectra, f32 SCM accumulation, f64 per-bin solve)",
-               "data": "synthetic", "config": config, "clocks": summarize_clocks(samples), "gpu_launches": launches_per_step * args.steps,
-               "roofline": roof}
+               "data": "synthetic", "config": config, "clocks": summarize_clocks(samples),
+               "gpu_launches": sum(k["launches"] for k in kernels) * chunks * args.steps, "roofline": roof}
         if e2e:
             res["e2e"] = e2e
         if not args.no_cpu and world == 1:      # the CPU leg is an N = 1 measurement (rank 0 owns the whole host)
-            res["cpu_baseline"] = cpu_baseline(K, C, L, n_fft, budget_s=12.0)
-            res["cpu_baseline_vectorized"] = cpu_baseline(K, C, L, n_fft, budget_s=6.0, granularity="bin")
+            arm = CpuArm(K, C, L, n_fft)
+            res["cpu_baseline"] = arm.sample(12.0)
+            res["cpu_baseline_vectorized"] = arm.sample(6.0, granularity="bin")
+            arm.close()
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()

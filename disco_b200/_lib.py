@@ -24,6 +24,16 @@ SIGNATURES = {
     "disco_stft_scm_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "disco_stft_scm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),
+    "disco_stft_scm_supported": (c_int, [c_int, c_int, c_int]),
+    "disco_stft_scm2_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "disco_stft_scm2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                c_size_t, c_void_p]),
+    "disco_scm_from_workspace": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
+    "disco_mwf_solve_workspace2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           c_double, c_void_p]),
+    "disco_filter_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_void_p]),
     "disco_tf_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p]),
     "disco_masked_scm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_int, c_int_p, c_int, c_void_p]),

@@ -54,8 +54,6 @@ int get_tables(int n_fft, Tables* out) {
         *out = it->second;
         return 0;
     }
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    (void)cs;
     const int RA = n_fft / 32;
     std::vector<float2> tw(n_fft);
     std::vector<float> wh(n_fft), w(n_fft);
@@ -82,14 +80,17 @@ int get_tables(int n_fft, Tables* out) {
     return 0;
 }
 
+// SM count of the CURRENT device (cached per device: processes may drive several GPUs)
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
     }
-    return n;
+    return cache[dev];
 }
 
 // Persistent launch geometry of the fused STFT kernel: one CTA per SM (fewer when there are fewer tiles).
@@ -105,12 +106,23 @@ StftPlan plan_stft(int n_grp, int C, int T, int n_fft) {
     return pl;
 }
 
-int stft_common(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_sig,
-                int C, int length, int n_fft, void* workspace, size_t workspace_bytes, bool scm, void* stream) {
+size_t stft_ws_bytes(int n_grp, int C, int length, int n_fft, int n_mask) {
+    if (!valid_nfft(n_fft) || C < 1 || C > 8 || n_grp < 1 || n_mask < 1) return 0;
+    const int T = disco_n_frames(length, n_fft);
+    const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
+    return (size_t)n_grp * pl.slots_per_grp * n_mask * 2 * C * C * (n_fft / 2 + 1) * sizeof(float);
+}
+
+int stft_common(const float* x, const float* mask, const float* mask2, int mask_layout, void* Y, void* Rss,
+                void* Rnn, int n_sig, int C, int length, int n_fft, void* workspace, size_t workspace_bytes, int n_mask,
+                void* stream) {
     if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
     if (n_sig <= 0 || length <= n_fft / 2)
         return fail(DISCO_ERR_INVALID, "need n_sig > 0 and length > n_fft/2 (reflect padding)");
-    if (C < 1 || C > 4) return fail(DISCO_ERR_UNSUPPORTED, "fused STFT+SCM supports 1..4 channels per group");
+    if (C < 1) return fail(DISCO_ERR_INVALID, "C must be positive");
+    if (!stft_scm_supported(n_fft, C, n_mask))
+        return fail(DISCO_ERR_UNSUPPORTED,
+                    "fused STFT+SCM: 1..8 channels per group (1..4 with two masks or n_fft = 1024)");
     if (!x || !Y) return fail(DISCO_ERR_INVALID, "null pointer");
     Tables tb;
     int rc = get_tables(n_fft, &tb);
@@ -121,6 +133,7 @@ int stft_common(const float* x, const float* mask, int mask_layout, void* Y, voi
     memset(&a, 0, sizeof(a));
     a.x = x;
     a.mask = mask;
+    a.mask2 = mask2;
     a.Y = (float2*)Y;
     a.part = (float*)workspace;
     a.twiddle = tb.twiddle;
@@ -131,22 +144,18 @@ int stft_common(const float* x, const float* mask, int mask_layout, void* Y, voi
     a.T = T;
     a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
     a.use_tma = (length % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    {
-        static const int dbg = getenv("DISCO_DBG") ? atoi(getenv("DISCO_DBG")) : 0;
-        a.dbg = dbg;
-    }
     const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
     a.slots_per_grp = pl.slots_per_grp;
     cudaStream_t st = (cudaStream_t)stream;
-    if (scm) {
-        if (!mask || (!Rss) != (!Rnn)) return fail(DISCO_ERR_INVALID, "null pointer");
-        const size_t need = disco_stft_scm_workspace(n_grp, C, length, n_fft);
+    if (n_mask > 0) {
+        if (!mask || (n_mask == 2 && !mask2) || (!Rss) != (!Rnn)) return fail(DISCO_ERR_INVALID, "null pointer");
+        const size_t need = stft_ws_bytes(n_grp, C, length, n_fft, n_mask);
         if (!workspace || workspace_bytes < need) return fail(DISCO_ERR_WORKSPACE, "workspace too small");
     }
-    CU(launch_stft_scm(a, n_fft, C, pl.n_cta, scm, st), "stft_scm launch");
-    if (scm && Rss)
+    CU(launch_stft_scm(a, n_fft, C, pl.n_cta, n_mask, st), "stft_scm launch");
+    if (n_mask == 1 && Rss)
         CU(launch_scm_finalize(a.part, (float2*)Rss, (float2*)Rnn, n_grp, pl.slots_per_grp, pl.tiles_per_grp,
-                               pl.n_cta, C, n_fft / 2 + 1, T, st),
+                               pl.n_cta, C, n_fft / 2 + 1, T, 1, 0, st),
            "scm_finalize launch");
     return 0;
 }
@@ -170,21 +179,44 @@ int disco_init(int n_fft) {
 int disco_stft(const float* x, void* Y, int n_sig, int length, int n_fft, void* stream) {
     // plain STFT: signals are grouped by 4 only to share a CTA's tile; groups are independent
     const int C = n_sig >= 4 ? 4 : n_sig;
-    return stft_common(x, nullptr, 0, Y, nullptr, nullptr, n_sig, C, length, n_fft, nullptr, 0, false, stream);
+    return stft_common(x, nullptr, nullptr, 0, Y, nullptr, nullptr, n_sig, C, length, n_fft, nullptr, 0, 0, stream);
 }
 
 size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft) {
-    if (!valid_nfft(n_fft) || C < 1 || n_grp < 1) return 0;
-    const int T = disco_n_frames(length, n_fft);
-    const StftPlan pl = plan_stft(n_grp, C > 4 ? 4 : C, T, n_fft);
-    return (size_t)n_grp * pl.slots_per_grp * 2 * C * C * (n_fft / 2 + 1) * sizeof(float);
+    return stft_ws_bytes(n_grp, C, length, n_fft, 1);
 }
+
+int disco_stft_scm_supported(int n_fft, int C, int n_mask) { return stft_scm_supported(n_fft, C, n_mask) ? 1 : 0; }
 
 int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn, int n_grp,
                    int C, int length, int n_fft, void* workspace, size_t workspace_bytes, void* stream) {
     if (n_grp <= 0) return fail(DISCO_ERR_INVALID, "n_grp must be positive");
-    return stft_common(x, mask, mask_layout, Y, Rss, Rnn, n_grp * C, C, length, n_fft, workspace, workspace_bytes,
-                       true, stream);
+    return stft_common(x, mask, nullptr, mask_layout, Y, Rss, Rnn, n_grp * C, C, length, n_fft, workspace,
+                       workspace_bytes, 1, stream);
+}
+
+size_t disco_stft_scm2_workspace(int n_grp, int C, int length, int n_fft) {
+    return stft_ws_bytes(n_grp, C, length, n_fft, 2);
+}
+
+int disco_stft_scm2(const float* x, const float* mask_a, const float* mask_b, int mask_layout, void* Y, int n_grp,
+                    int C, int length, int n_fft, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_grp <= 0) return fail(DISCO_ERR_INVALID, "n_grp must be positive");
+    return stft_common(x, mask_a, mask_b, mask_layout, Y, nullptr, nullptr, n_grp * C, C, length, n_fft, workspace,
+                       workspace_bytes, 2, stream);
+}
+
+int disco_scm_from_workspace(const void* workspace, int n_set, int set, void* Rss, void* Rnn, int n_grp, int C,
+                             int length, int n_fft, void* stream) {
+    if (!valid_nfft(n_fft) || n_grp < 1 || C < 1 || C > 8 || n_set < 1 || n_set > 2 || set < 0 || set >= n_set ||
+        !workspace || !Rss || !Rnn)
+        return fail(DISCO_ERR_INVALID, "bad arguments");
+    const int T = disco_n_frames(length, n_fft);
+    const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
+    CU(launch_scm_finalize((const float*)workspace, (float2*)Rss, (float2*)Rnn, n_grp, pl.slots_per_grp,
+                           pl.tiles_per_grp, pl.n_cta, C, n_fft / 2 + 1, T, n_set, set, (cudaStream_t)stream),
+       "scm_finalize launch");
+    return 0;
 }
 
 int disco_tf_mask(const void* S, const void* N, float* M, size_t n_elem, int kind, int power, float bin_thr_db,
@@ -289,10 +321,11 @@ int disco_tango_mid(const void* W1, const void* Y, const float* mask_w, void* Z,
     return 0;
 }
 
-int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp, int C,
-                              int length, int n_fft, int filter_type, int rank, double mu, void* stream) {
+static int solve_workspace(const void* workspace, int n_set, void* W, void* T1, void* Rss, void* Rnn, int n_grp, int C,
+                           int length, int n_fft, int filter_type, int rank, double mu, void* stream) {
     if (filter_type < 0 || filter_type > 2) return fail(DISCO_ERR_INVALID, "Unknown filter reference");
-    if (!valid_nfft(n_fft) || n_grp < 1 || C < 1 || C > 4 || !workspace || !W || (!Rss) != (!Rnn))
+    if (!valid_nfft(n_fft) || n_grp < 1 || C < 1 || C > 4 || n_set < 1 || n_set > 2 || !workspace || !W ||
+        (!Rss) != (!Rnn))
         return fail(DISCO_ERR_INVALID, "bad arguments");
     const int T = disco_n_frames(length, n_fft), F = n_fft / 2 + 1;
     const StftPlan pl = plan_stft(n_grp, C, T, n_fft);
@@ -302,7 +335,8 @@ int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rs
     a.Rnn = (const float2*)Rnn;
     a.W = (float2*)W;
     a.T1 = (float2*)T1;
-    a.n_mat = n_grp * F;
+    a.n_mat = n_set * n_grp * F;
+    a.n_set = n_set;
     a.D = C;
     a.type = filter_type;
     a.rank = rank;
@@ -315,6 +349,17 @@ int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rs
     a.inv_T = 1.0f / (float)T;
     CU(launch_mwf_solve(a, (cudaStream_t)stream), "mwf_solve launch");
     return 0;
+}
+
+int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp, int C,
+                              int length, int n_fft, int filter_type, int rank, double mu, void* stream) {
+    return solve_workspace(workspace, 1, W, T1, Rss, Rnn, n_grp, C, length, n_fft, filter_type, rank, mu, stream);
+}
+
+int disco_mwf_solve_workspace2(const void* workspace, void* W, void* T1, int n_grp, int C, int length, int n_fft,
+                               int filter_type, int rank, double mu, void* stream) {
+    return solve_workspace(workspace, 2, W, T1, nullptr, nullptr, n_grp, C, length, n_fft, filter_type, rank, mu,
+                           stream);
 }
 
 int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_mat, int D, int filter_type,
@@ -353,6 +398,30 @@ int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, vo
     a.ref = ref;
     a.out_ft = (out_layout == DISCO_LAYOUT_FT);
     CU(launch_filter_sum(a, (cudaStream_t)stream), "filter_sum launch");
+    return 0;
+}
+
+int disco_filter_dual(const void* W1, const void* W2, const void* Y, void* z, void* zn, void* yf, int ref,
+                      int out_layout, int n_grp, int C, int T, int n_fft, void* stream) {
+    if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (!W1 || !W2 || !Y || !z || !yf || n_grp < 1 || T < 1) return fail(DISCO_ERR_INVALID, "bad arguments");
+    if (C < 1 || C > 4) return fail(DISCO_ERR_UNSUPPORTED, "filter_dual supports 1..4 channels");
+    if (ref < 0 || ref >= C) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    if (n_grp > 65535) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 groups per call");
+    DualFilterArgs a;
+    a.Y = (const float2*)Y;
+    a.W1 = (const float2*)W1;
+    a.W2 = (const float2*)W2;
+    a.z = (float2*)z;
+    a.zn = (float2*)zn;
+    a.yf = (float2*)yf;
+    a.n_grp = n_grp;
+    a.C = C;
+    a.T = T;
+    a.F = n_fft / 2 + 1;
+    a.ref = ref;
+    a.out_ft = (out_layout == DISCO_LAYOUT_FT);
+    CU(launch_filter_dual(a, sm_count(), (cudaStream_t)stream), "filter_dual launch");
     return 0;
 }
 

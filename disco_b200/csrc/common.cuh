@@ -10,12 +10,28 @@ namespace disco {
 // ---------------------------------------------------------------- complex helpers (float2)
 DISCO_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 DISCO_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// Complex products on the packed FP32 pipe: one FMUL2 + one FFMA2 each.  ptxas folds the half swaps
+// and sign flips into operand modifiers when the modified VECTOR is the first operand and the
+// broadcast scalar the second (the other order costs two extra instructions).
+// Rounding: re = fma(a.x, b.x, -(a.y b.y)), im = fma(a.x, b.y, a.y b.x).
 DISCO_DEV float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+    const float2 t = __fmul2_rn(make_float2(-b.y, b.x), make_float2(a.y, a.y));
+    return __ffma2_rn(b, make_float2(a.x, a.x), t);
 }
-// a * conj(b)
+// a * conj(b):  re = fma(a.x, b.x, a.y b.y), im = fma(a.y, b.x, -(a.x b.y))
 DISCO_DEV float2 cmulc(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+    const float2 t = __fmul2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y));
+    return __ffma2_rn(a, make_float2(b.x, b.x), t);
+}
+// acc + a * b  (two FFMA2)
+DISCO_DEV float2 cfma(float2 a, float2 b, float2 acc) {
+    const float2 t = __ffma2_rn(b, make_float2(a.x, a.x), acc);
+    return __ffma2_rn(make_float2(-b.y, b.x), make_float2(a.y, a.y), t);
+}
+// acc + conj(a) * b  (two FFMA2): the filter-and-sum term  conj(w) x
+DISCO_DEV float2 cfma_cj(float2 a, float2 b, float2 acc) {
+    const float2 t = __ffma2_rn(b, make_float2(a.x, a.x), acc);
+    return __ffma2_rn(make_float2(b.y, -b.x), make_float2(a.y, a.y), t);
 }
 DISCO_DEV float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 DISCO_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }

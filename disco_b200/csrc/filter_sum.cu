@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) filter_sum_kernel(FilterArgs a, int frame
                     cr[i] = a.resid ? refch[(size_t)t * F] : make_float2(0.f, 0.f);
                 }
 #pragma unroll
-                for (int d = 0; d < D; ++d) acc = cadd(acc, cmul(w[d], cx[i][d]));
+                for (int d = 0; d < D; ++d) acc = cfma(w[d], cx[i][d], acc);
                 if (a.resid) r = csub(cr[i], acc);
                 if (!a.out_ft && active) {
                     a.out[((size_t)grp * T + t) * F + f] = acc;
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256, (D <= 4 ? 2 : 1)) filter_sum_tf_kernel(Fi
         for (int u = 0; u < UF; ++u) {
             const int tt = t + u * TS;
             if (tt < t_end) {
-                float2 acc = cmul(w[0], x[u][0]);
+                float2 acc = cfma(w[0], x[u][0], make_float2(0.f, 0.f));
 #pragma unroll
-                for (int d = 1; d < D; ++d) acc = cadd(acc, cmul(w[d], x[u][d]));
+                for (int d = 1; d < D; ++d) acc = cfma(w[d], x[u][d], acc);
                 out[tt * F] = acc;
                 if (res) res[tt * F] = csub(r[u], acc);
             }

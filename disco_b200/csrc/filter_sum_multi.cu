@@ -78,19 +78,19 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
                 const int k = item % K, ts = item / K;
                 const float2* wk = ws + k * D * 32 + lane;
                 const float2* yk = xs + (k * C * TS + ts) * 32;
-                float2 acc = cmul(wk[0], yk[0]);
+                float2 acc = cfma(wk[0], yk[0], make_float2(0.f, 0.f));
                 float2 xr = yk[0];
 #pragma unroll
                 for (int c = 1; c < C; ++c) {
                     const float2 x = yk[c * TS * 32];
-                    acc = cadd(acc, cmul(wk[c * 32], x));
+                    acc = cfma(wk[c * 32], x, acc);
                     if (c == a.ref) xr = x;
                 }
 #pragma unroll
                 for (int r = 0; r < K - 1; ++r) {      // reference order: nodes < k, then nodes > k
                     const int j = r + (r >= k ? 1 : 0);
                     const float2 x = xs[((K * C + j) * TS + ts) * 32];
-                    acc = cadd(acc, cmul(wk[(C + r) * 32], x));
+                    acc = cfma(wk[(C + r) * 32], x, acc);
                     if (C + r == a.ref) xr = x;
                 }
                 const int t = (tile0 + i) * tspan + lg.tl + ts * lg.tmul;

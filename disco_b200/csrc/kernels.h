@@ -8,20 +8,24 @@ namespace disco {
 struct StftArgs {
     const float* x;         // [n_sig][L] float32 time signals (n_sig = n_grp * C, last group may be short)
     const float* mask;      // SCM only: [n_grp][T][F] (mask_ft = 0) or [n_grp][F][T] (mask_ft = 1)
+    const float* mask2;     // two-mask SCM only: the second mask, same layout
     float2* Y;              // [n_sig][T][F] complex64, frame-major
-    float* part;            // SCM only: [n_grp][slots_per_grp][2 C^2][F] partial sums per (group, CTA) segment
+    float* part;            // SCM only: [n_grp][slots_per_grp][n_mask][2 C^2][F] partial sums per (group, CTA) segment
     const float2* twiddle;  // [N/32][32]: W_N^(l*k1)
     const float* window;    // [N]: 0.5 * periodic Hann
     int n_sig, n_grp, L, T;
     int slots_per_grp;
     int mask_ft;
     int use_tma;
-    int dbg;                // profiling experiments only (DISCO_DBG env): 1 no Y stores, 2 no SCM math, 4 no FFT math
 };
 
-cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool scm, cudaStream_t st);
+// n_mask: 0 plain STFT, 1 STFT + SCMs under `mask`, 2 STFT + SCMs under `mask` and `mask2`
+cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, int n_mask, cudaStream_t st);
+bool stft_scm_supported(int n_fft, int C, int n_mask);
+// matrices of mask set `set` (of n_set) from the segment partial sums
 cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int slots_per_grp,
-                                int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st);
+                                int tiles_per_grp, int n_cta, int C, int F, int T, int n_set, int set, cudaStream_t st);
+int stft_tile_frames(int n_fft, int C);
 int stft_tiles_per_grp(int n_fft, int C, int T);
 int stft_slots_per_grp(int n_grp, int tiles_per_grp, int n_cta);
 int stft_cta_of_tile_host(long long i, long long total, int nb);
@@ -65,9 +69,10 @@ struct SolveArgs {
     int rank;            // gevd: number of generalised eigenpairs kept; <= 0 or >= D means full
     double mu;
     // optional: read the matrices straight from the fused STFT+SCM kernel's segment partial sums
-    // (skips scm_finalize); matrix idx = grp * F + f
-    const float* part;   // [n_grp][slots_per_grp][2 D^2][F] or null
+    // (skips scm_finalize); matrix idx = (set * n_grp + grp) * F + f, n_mat = n_set * n_grp * F
+    const float* part;   // [n_grp][slots_per_grp][n_set][2 D^2][F] or null
     int slots_per_grp, tiles_per_grp, n_cta, F;
+    int n_set;           // mask sets in the partial sums (0 is read as 1)
     float inv_T;
 };
 cudaError_t launch_mwf_solve(const SolveArgs& a, cudaStream_t st);
@@ -83,6 +88,18 @@ struct FilterArgs {
 };
 cudaError_t launch_filter_sum(const FilterArgs& a, cudaStream_t st);
 cudaError_t launch_filter_sum_multi(const FilterArgs& a, cudaStream_t st);   // K > 1, all nodes, TF output
+
+// Single-node groups, both filters in one pass over Y (filter_dual.cu): z = w1^H y, zn = y[ref] - z, yf = w2^H y
+struct DualFilterArgs {
+    const float2* Y;     // [n_grp][C][T][F]
+    const float2* W1;    // [n_grp][F][C] step-1 filters
+    const float2* W2;    // [n_grp][F][C] step-2 filters
+    float2* z;           // [n_grp][T][F] (out_ft = 0) or [n_grp][F][T]
+    float2* zn;          // same layout, may be null
+    float2* yf;          // same layout
+    int n_grp, C, T, F, ref, out_ft;
+};
+cudaError_t launch_filter_dual(const DualFilterArgs& a, int sm_count, cudaStream_t st);
 
 // Fused multi-node middle pass (mid_multi.cu): z, zn of every node + step-2 SCMs of every node.
 struct MidArgs {

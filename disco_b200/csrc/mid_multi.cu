@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(32 * KS * NPART, MINB) tango_mid_kernel(MidArg
                 const float2* yj = ys + (j * C * TS + ts) * 32;
                 const float2* wj = w1s + j * C * 32 + lane;
                 float2 y0 = yj[0];
-                float2 z = cmul(wj[0], y0), yr = y0;
+                float2 z = cfma(wj[0], y0, make_float2(0.f, 0.f)), yr = y0;
 #pragma unroll
                 for (int c = 1; c < C; ++c) {
                     const float2 yc = yj[c * TS * 32];
-                    z = cadd(z, cmul(wj[c * 32], yc));
+                    z = cfma(wj[c * 32], yc, z);
                     if (c == a.ref) yr = yc;
                 }
                 zt[(ts * K + j) * 32] = z;

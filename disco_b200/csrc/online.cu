@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(32 * kOnlineBY) filter_sum_blocks_kernel(Onlin
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const float2 x = ch[d][(size_t)t * F];
-            z = cadd(z, cmul(w[d], x));
+            z = cfma(w[d], x, z);
             if (d == a.ref) yr = x;
         }
         const size_t o = ((size_t)grp * T + t) * F + f;

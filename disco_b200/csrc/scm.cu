@@ -105,9 +105,9 @@ DISCO_DEV void scm_accumulate(const ScmArgs& a, int grp, int f, bool active, int
         const float wa = m * m, wb = mrow ? (1.f - m) * (1.f - m) : 0.f;
         PairAcc<D, PART, 0>::run(y, wa, wb, ps, pn);
         if (zfuse && active) {
-            float2 z = cmul(w1[0], y[0]);
+            float2 z = cfma(w1[0], y[0], make_float2(0.f, 0.f));
 #pragma unroll
-            for (int d = 1; d < D; ++d) z = cadd(z, cmul(w1[d], y[d]));
+            for (int d = 1; d < D; ++d) z = cfma(w1[d], y[d], z);
             zrow[t * F] = z;
             if (znrow) {
                 float2 r = y[0];

@@ -56,10 +56,10 @@ DISCO_DEV void wide_tile(const ScmArgs& a, const float2* yb, const float* mb, co
         // (every partition holds all D operands), which balances the extra work over the partitions
         if (ZF && (s % NPART == PART)) {
             const int t = tfirst + s * TW * lg.tmul;
-            float2 z = cmul(w1s[0], x[0]), yr = x[0];
+            float2 z = cfma(w1s[0], x[0], make_float2(0.f, 0.f)), yr = x[0];
 #pragma unroll
             for (int d = 1; d < D; ++d) {
-                z = cadd(z, cmul(w1s[d * 32], x[d]));
+                z = cfma(w1s[d * 32], x[d], z);
                 if (d == a.ref) yr = x[d];
             }
             if (lg.ok && t < a.in.T) {

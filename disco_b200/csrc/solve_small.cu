@@ -263,12 +263,14 @@ __global__ void __launch_bounds__(64, MINB) mwf_solve_kernel(SolveArgs a) {
     cd w[D], t1[D];
     for (int i = 0; i < D; ++i) t1[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);   // e_0 (internal_formulas.py:43)
     if (PART) {
-        const int g = idx / a.F, f = idx % a.F;
-        const long long total = (long long)(a.n_mat / a.F) * a.tiles_per_grp;
+        const int n_set = a.n_set > 0 ? a.n_set : 1;
+        const int n_grp = a.n_mat / (a.F * n_set);
+        const int set = idx / (n_grp * a.F), g = (idx / a.F) % n_grp, f = idx % a.F;
+        const long long total = (long long)n_grp * a.tiles_per_grp;
         const int b_first = cta_of_tile_dev((long long)g * a.tiles_per_grp, total, a.n_cta);
         const int n_slot = cta_of_tile_dev((long long)(g + 1) * a.tiles_per_grp - 1, total, a.n_cta) - b_first + 1;
-        const size_t slot_stride = (size_t)2 * D * D * a.F;
-        const float* q = a.part + (size_t)g * a.slots_per_grp * slot_stride + f;
+        const size_t slot_stride = (size_t)n_set * 2 * D * D * a.F;
+        const float* q = a.part + (size_t)g * a.slots_per_grp * slot_stride + (size_t)set * 2 * D * D * a.F + f;
         load_part<D>(q, n_slot, slot_stride, a.F, a.inv_T, S);
         load_part<D>(q + (size_t)D * D * a.F, n_slot, slot_stride, a.F, a.inv_T, Nn);
         if (a.Rss) {   // optionally also materialise the matrices (API output of the fused op)

@@ -2,8 +2,11 @@
 //
 // Replaces, for a whole batch in one launch:
 //   lb.core.stft(x, n_fft, hop, center=True)            reference tango.py:335-337
-//   s_hat = m * Y, n_hat = (1 - m) * Y                   reference tango.py:347-348
-//   np.outer(.., conj(..)) per (f, t) + np.mean over t   reference tango.py:357-364
+//   s_hat = m * Y, n_hat = (1 - m) * Y                   reference tango.py:347-348, :413-414
+//   np.outer(.., conj(..)) per (f, t) + np.mean over t   reference tango.py:357-364, :433-440
+// for up to 8 microphones per array node and for ONE or TWO masks at once (NM = 2: the step-1 mask
+// AND the step-2 mask of a single-node array, whose step-2 input is the same Y -- tango.py:431-440
+// with K = 1 -- so Y never has to be read back for the second set of statistics).
 //
 // Persistent, warp-specialised kernel: one CTA per SM walks a contiguous range of TILES
 // (tile = TT consecutive frames of one group; group = one array node of one utterance, C mics).
@@ -11,74 +14,168 @@
 // mbarriers (no __syncthreads in the steady state):
 //
 //   warp 0        LOADER   stages the (TT+1)*hop samples of every channel with one 1-D bulk TMA
-//                          copy per channel (edge tiles: scalar loads with librosa's reflect
-//                          padding), one tile ahead.  It also owns the Nyquist bin (lanes <-> frames).
-//   warps 1..8    FFT      two real channels are transformed by ONE complex FFT.  A warp computes
-//                          32/RA transforms per job (RA = N/32): an RA-point in-register DFT per
-//                          lane, a padded transposition through shared memory, then one 32-point
-//                          in-register DFT per lane.  Spectra of the channel pairs stay in smem.
-//   warps 9..     SCM      thread f owns frequency bin f.  It un-mixes the two-for-one spectra,
-//                          writes Y (frame-major rows, coalesced), and accumulates the Hermitian
-//                          upper triangles of  sum_t m^2 y y^H  and  sum_t (1-m)^2 y y^H  in
-//                          registers (one outer product feeds both).  Mask values are prefetched
-//                          one tile ahead.
+//                          copy per channel (edge tiles: the FFT warps fill in librosa's reflect
+//                          padding), one tile ahead.  It also owns the Nyquist bin: lanes <-> channel
+//                          PAIRS (the Nyquist spectrum is real, an SCM entry a plain product).
+//   FFT warps     two real channels are transformed by ONE complex FFT.  A job is 32/RA transforms
+//                          (RA = N/32): an RA-point in-register DFT per lane, a padded transposition
+//                          through shared memory, then one 32-point in-register DFT per lane, all on
+//                          the packed FP32 pipe (fft_reg.cuh).  Spectra of the pairs stay in smem.
+//   SCM warps     thread f owns frequency bin f.  It un-mixes the two-for-one spectra, writes Y
+//                          (frame-major rows, coalesced), and accumulates the Hermitian upper
+//                          triangles of  sum_t m^2 y y^H  and  sum_t (1-m)^2 y y^H  (per mask) in
+//                          registers: one packed outer product (FMUL2 + FFMA2) feeds all of them.
+//                          Mask values are prefetched a chunk of frames ahead.
+// For 5..8 microphones the 128 accumulators of a bin need ~184 registers, so the roles are laid out
+// on warpgroup boundaries and the register file is redistributed with setmaxnreg (loader 40, FFT 96,
+// SCM 184) -- the same mechanism the TMA/MMA kernels of this architecture use.
 //
 // A CTA's tile range may cross group boundaries; accumulators are flushed per (group, CTA)
-// segment into a small workspace and reduced in fixed order by scm_finalize_kernel
-// (deterministic, no atomics).
+// segment into a small workspace and reduced in fixed order by scm_finalize_kernel or directly by
+// the solver (deterministic, no atomics).
 #include "common.cuh"
 #include "fft_reg.cuh"
 #include "kernels.h"
 
 namespace disco {
 
-template <int N>
-struct FftGeom {
+template <int N, int C>
+struct StftCfg {
     static constexpr int RA = N / 32;              // radix of the per-lane first pass
     static constexpr int NB = 32 / RA;             // transforms per warp job
     static constexpr int HALF = N / 2;             // hop (50 % overlap)
     static constexpr int F = N / 2 + 1;            // bins
-    static constexpr int FFT_WARPS = 8;            // one job per FFT warp per tile
-    static constexpr int ITEMS = FFT_WARPS * NB;   // (frame, channel-pair) transforms per tile
+    static constexpr int JOBS = 8;                 // jobs per tile
+    static constexpr int ITEMS = JOBS * NB;        // (frame, channel-pair) transforms per tile
+    static constexpr int P = (C + 1) / 2;          // channel pairs per frame
+    static constexpr int TT = ITEMS / P;           // frames per tile
+    static constexpr bool WIDE = C > 4;            // 128 accumulators per bin
+    // Roles on warpgroup boundaries + setmaxnreg: the SCM warps of wide arrays (128 accumulators) and of
+    // two-mask runs (64) need more registers than an even split of the register file gives them.
+    static constexpr bool REALLOC = (N == 512) || (WIDE && N == 256);
+    static constexpr int FFT_WARPS = (WIDE && N == 512) ? 4 : 8;
+    static constexpr int JPW = JOBS / FFT_WARPS;   // jobs per FFT warp and tile
     static constexpr int ROWP = 1056 / NB;         // spectrum row pitch (complex): a job = 32 x 33 scratch
     static constexpr int SCM_WARPS = N / 64;       // bins 0 .. N/2-1, one per thread
-    static constexpr int WARPS = 1 + FFT_WARPS + SCM_WARPS;
+    static constexpr int LEAD_WARPS = REALLOC ? 4 : 1;   // warp 0 = loader; 1..3 idle (warpgroup padding)
+    static constexpr int WARPS = LEAD_WARPS + FFT_WARPS + SCM_WARPS;
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int SPEC = ITEMS * ROWP;      // complex per spectrum stage
+    static constexpr int SAMP = C * (TT + 1) * HALF;   // floats per sample stage
+    // registers per thread at launch: each of the 4 SM sub-partitions holds 16384 registers and ceil(WARPS/4) warps
+    static constexpr int REG_LAUNCH = 16384 / ((WARPS + 3) / 4) / 32 / 8 * 8;
+    static constexpr int REG_LEAD = 40, REG_FFT = 96, REG_SCM = WIDE ? 184 : 120;   // REALLOC only
+    static constexpr int REG_SUM = 128 * REG_LEAD + 32 * FFT_WARPS * REG_FFT + 32 * SCM_WARPS * REG_SCM;
+    static_assert(!REALLOC || REG_SUM <= (REG_LAUNCH > 255 ? 255 : REG_LAUNCH) * THREADS,
+                  "register budgets exceed the CTA's allocation");
 };
 
-template <int N>
-__host__ __device__ constexpr int tile_frames_n(int C) { return FftGeom<N>::ITEMS / ((C + 1) / 2); }
+int stft_tile_frames(int n_fft, int C) { return (8 * (32 / (n_fft / 32))) / ((C + 1) / 2); }
 
-template <int N>
-__host__ __device__ inline size_t smem_bytes(int C) {
-    using G = FftGeom<N>;
-    const size_t spec = 2 * (size_t)G::SPEC * sizeof(float2);
-    const size_t samp = 2 * (size_t)C * (tile_frames_n<N>(C) + 1) * G::HALF * sizeof(float);
-    const size_t tw = (size_t)N * sizeof(float2);
-    return spec + samp + tw + 128;
+template <int N, int C>
+__host__ __device__ inline size_t smem_bytes() {
+    using G = StftCfg<N, C>;
+    return 2 * (size_t)G::SPEC * sizeof(float2) + 2 * (size_t)G::SAMP * sizeof(float) + (size_t)N * sizeof(float2) + 128 +
+           64 * sizeof(float);
 }
 
 __device__ __forceinline__ long long range_lo(long long total, int b, int nb) { return total * b / nb; }
 
 // first CTA whose tile range contains tile i
-__device__ __forceinline__ int cta_of_tile(long long i, long long total, int nb) {
+__host__ __device__ __forceinline__ int cta_of_tile(long long i, long long total, int nb) {
     int b = (int)((i * nb) / total);
     if (b >= nb) b = nb - 1;
-    while (b + 1 < nb && range_lo(total, b + 1, nb) <= i) ++b;
-    while (b > 0 && range_lo(total, b, nb) > i) --b;
+    while (b + 1 < nb && total * (b + 1) / nb <= i) ++b;
+    while (b > 0 && total * b / nb > i) --b;
     return b;
 }
 
-template <int N, int C, bool SCM>
-__global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftArgs p) {
-    using G = FftGeom<N>;
-    constexpr int RA = G::RA, NB = G::NB, H = G::HALF, F = G::F, ROWP = G::ROWP;
-    constexpr int P = (C + 1) / 2;            // channel pairs per frame
-    constexpr int TT = G::ITEMS / P;          // frames per tile
-    constexpr int NOFF = C * (C - 1) / 2;
-    constexpr int SAMP = C * (TT + 1) * H;    // floats per sample stage
-    constexpr int NACC = 2 * C * C;
+template <int R>
+DISCO_DEV void set_maxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R));
+}
+template <int R>
+DISCO_DEV void set_maxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(R));
+}
+
+// Accumulators of one bin: per mask, C diagonal pairs (s-weighted, n-weighted) and C(C-1)/2
+// complex off-diagonal sums for each of the two weights.
+template <int C, int NM>
+struct ScmAcc {
+    static constexpr int NOFF = C * (C - 1) / 2;
+    static constexpr int NO = NOFF > 0 ? NOFF : 1;
+    float2 d[NM > 0 ? NM : 1][C];     // (sum m^2 |y_i|^2, sum (1-m)^2 |y_i|^2)
+    float2 os[NM > 0 ? NM : 1][NO];   // sum m^2 y_i conj(y_j), i < j row-major
+    float2 on[NM > 0 ? NM : 1][NO];   // sum (1-m)^2 y_i conj(y_j)
+    DISCO_DEV void reset() {
+#pragma unroll
+        for (int q = 0; q < NM; ++q) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) d[q][i] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < NOFF; ++i) os[q][i] = on[q][i] = make_float2(0.f, 0.f);
+        }
+    }
+    // one (frame, bin) point: masks m[q]
+    DISCO_DEV void step(const float2 (&y)[C], const float (&m)[NM > 0 ? NM : 1]) {
+        float2 ab[NM > 0 ? NM : 1];
+#pragma unroll
+        for (int q = 0; q < NM; ++q) {
+            const float om = 1.f - m[q];
+            ab[q] = make_float2(m[q] * m[q], om * om);
+        }
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const float dd = fmaf(y[i].x, y[i].x, y[i].y * y[i].y);
+#pragma unroll
+            for (int q = 0; q < NM; ++q) d[q][i] = __ffma2_rn(make_float2(dd, dd), ab[q], d[q][i]);
+#pragma unroll
+            for (int j = i + 1; j < C; ++j) {
+                const float2 op = cmulc(y[i], y[j]);
+#pragma unroll
+                for (int q = 0; q < NM; ++q) {
+                    os[q][o] = cfma_r(ab[q].x, op, os[q][o]);
+                    on[q][o] = cfma_r(ab[q].y, op, on[q][o]);
+                }
+                ++o;
+            }
+        }
+    }
+    // rows of the workspace for bin f: per mask [s: C diag, NOFF x (re, im)][n: the same]
+    DISCO_DEV void flush(float* out, int F) const {
+        int a = 0;
+#pragma unroll
+        for (int q = 0; q < NM; ++q) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) out[(size_t)(a++) * F] = d[q][i].x;
+#pragma unroll
+            for (int i = 0; i < NOFF; ++i) {
+                out[(size_t)(a++) * F] = os[q][i].x;
+                out[(size_t)(a++) * F] = os[q][i].y;
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) out[(size_t)(a++) * F] = d[q][i].y;
+#pragma unroll
+            for (int i = 0; i < NOFF; ++i) {
+                out[(size_t)(a++) * F] = on[q][i].x;
+                out[(size_t)(a++) * F] = on[q][i].y;
+            }
+        }
+    }
+};
+
+template <int N, int C, int NM>
+__global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(StftArgs p) {
+    using G = StftCfg<N, C>;
+    constexpr int RA = G::RA, NB = G::NB, H = G::HALF, F = G::F, ROWP = G::ROWP, P = G::P, TT = G::TT;
+    constexpr int SAMP = G::SAMP;
+    constexpr int NACC = NM * 2 * C * C;
+    constexpr int NMX = NM > 0 ? NM : 1;
+    constexpr bool SCM = NM > 0;
+    constexpr int MC = (TT * NM <= 8) ? TT : ((8 / NMX) < TT ? (8 / NMX) : TT);   // frames per mask chunk
+    constexpr int NCH = (TT + MC - 1) / MC;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* spec = reinterpret_cast<float2*>(smem_raw);                  // [2][ITEMS][ROWP]
@@ -89,6 +186,8 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
     uint64_t* samp_empty = bars + 2;   // [2]  FFT -> loader   (FFT_WARPS arrivals)
     uint64_t* spec_full = bars + 4;    // [2]  FFT -> SCM      (FFT_WARPS arrivals)
     uint64_t* spec_empty = bars + 6;   // [2]  SCM -> FFT      (SCM_WARPS + 1 arrivals)
+    float* nyq = reinterpret_cast<float*>(bars + 16);   // [TT * C <= 64] Nyquist-bin values of the current tile
+    static_assert(TT * C <= 64 && TT <= 32, "Nyquist staging");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, T = p.T;
@@ -110,171 +209,173 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
     }
     __syncthreads();
 
-    // SCM accumulators, flushed to the workspace at the end of every (group, CTA) segment
-    float ps_d[C], pn_d[C];
-    float2 ps_o[NOFF > 0 ? NOFF : 1], pn_o[NOFF > 0 ? NOFF : 1];
-    auto acc_reset = [&]() {
-#pragma unroll
-        for (int i = 0; i < C; ++i) ps_d[i] = pn_d[i] = 0.f;
-#pragma unroll
-        for (int i = 0; i < NOFF; ++i) ps_o[i] = pn_o[i] = make_float2(0.f, 0.f);
+    auto tile_of = [&](int it, int& grp, int& t0) {
+        const long long i = lo + it;
+        grp = (int)(i / tiles_per_grp);
+        t0 = (int)(i % tiles_per_grp) * TT;
     };
-    auto acc_step = [&](const float2 (&y)[C], float m) {
-        const float a = m * m, b = (1.f - m) * (1.f - m);
-        int o = 0;
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            const float d = fmaf(y[i].x, y[i].x, y[i].y * y[i].y);
-            ps_d[i] = fmaf(a, d, ps_d[i]);
-            pn_d[i] = fmaf(b, d, pn_d[i]);
-#pragma unroll
-            for (int j = i + 1; j < C; ++j) {
-                const float2 op = cmulc(y[i], y[j]);
-                ps_o[o] = cfma_r(a, op, ps_o[o]);
-                pn_o[o] = cfma_r(b, op, pn_o[o]);
-                ++o;
-            }
-        }
+    auto seg_slot = [&](int grp) {
+        return blockIdx.x - cta_of_tile((long long)grp * tiles_per_grp, total, gridDim.x);
     };
-    // write this thread's accumulators for bin f into the segment's slot
-    auto acc_flush = [&](int grp, int f) {
-        const int slot = blockIdx.x - cta_of_tile((long long)grp * tiles_per_grp, total, gridDim.x);
-        float* out = p.part + ((size_t)grp * p.slots_per_grp + slot) * NACC * F + f;
-        int a = 0;
-#pragma unroll
-        for (int i = 0; i < C; ++i) out[(size_t)(a++) * F] = ps_d[i];
-#pragma unroll
-        for (int i = 0; i < NOFF; ++i) {
-            out[(size_t)(a++) * F] = ps_o[i].x;
-            out[(size_t)(a++) * F] = ps_o[i].y;
-        }
-#pragma unroll
-        for (int i = 0; i < C; ++i) out[(size_t)(a++) * F] = pn_d[i];
-#pragma unroll
-        for (int i = 0; i < NOFF; ++i) {
-            out[(size_t)(a++) * F] = pn_o[i].x;
-            out[(size_t)(a++) * F] = pn_o[i].y;
-        }
-    };
-    // un-mix the two-for-one spectra of frame tl, bin f (window carries the 1/2):
-    //   A = Z[f] + conj(Z[N-f]),  B = -i (Z[f] - conj(Z[N-f]))
-    auto unmix = [&](const float2* stage, int tl, int f, float2 (&y)[C]) {
-        const int fn = (N - f) & (N - 1);
-#pragma unroll
-        for (int pr = 0; pr < P; ++pr) {
-            const float2* row = stage + (size_t)(tl * P + pr) * ROWP;
-            const float2 zf = row[f], zn = row[fn];
-            y[2 * pr] = make_float2(zf.x + zn.x, zf.y - zn.y);
-            if (2 * pr + 1 < C) y[2 * pr + 1] = make_float2(zf.y + zn.y, zn.x - zf.x);
-        }
+    auto mask_at = [&](int q, int grp, int t, int f) {
+        const float* m = q == 0 ? p.mask : p.mask2;
+        return p.mask_ft ? m[((size_t)grp * F + f) * T + t] : m[((size_t)grp * T + t) * F + f];
     };
 
-    if (warp == 0) {
+    if (warp < G::LEAD_WARPS) {
+        if (G::REALLOC) set_maxnreg_dec<G::REG_LEAD>();
+        if (warp != 0) return;
         // =========================================================== LOADER (+ Nyquist bin)
         auto load_tile = [&](int it) {
-            const long long i = lo + it;
-            const int grp = (int)(i / tiles_per_grp), t0 = (int)(i % tiles_per_grp) * TT;
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
             mbar_wait(&samp_empty[s], ((it >> 1) & 1) ^ 1);
             const float* xg = p.x + (size_t)grp * C * L;
             float* dst = samp + s * SAMP;
             const int s0 = t0 * H - H;
-            const bool interior = p.use_tma && nfr == TT && s0 >= 0 && s0 + (TT + 1) * H <= L;
-            if (interior) {
-                if (lane == 0) {
+            // the in-range part [k_lo, k_hi) of the tile's samples comes by TMA; the FFT warps fill the
+            // mirrored samples of edge tiles (at most one hop per side) themselves
+            const int cnt = (nfr + 1) * H;
+            const int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);
+            if (lane == 0) {
+                if (p.use_tma && k_hi > k_lo) {
                     fence_proxy_async();
-                    mbar_expect_tx(&samp_full[s], (uint32_t)(c_valid * (TT + 1) * H * sizeof(float)));
+                    mbar_expect_tx(&samp_full[s], (uint32_t)(c_valid * (k_hi - k_lo) * sizeof(float)));
                     for (int c = 0; c < c_valid; ++c)
-                        tma_load_1d(dst + c * (TT + 1) * H, xg + (size_t)c * L + s0,
-                                    (uint32_t)((TT + 1) * H * sizeof(float)), &samp_full[s]);
-                }
-            } else {
-                // edge tile (reflect padding / short tail): the in-range part [k_lo, k_hi) still comes by
-                // TMA; the FFT warps fill the mirrored samples (at most one hop per side) themselves.
-                const int cnt = (nfr + 1) * H;
-                const int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);
-                if (lane == 0) {
-                    if (p.use_tma && k_hi > k_lo) {
-                        fence_proxy_async();
-                        mbar_expect_tx(&samp_full[s], (uint32_t)(c_valid * (k_hi - k_lo) * sizeof(float)));
-                        for (int c = 0; c < c_valid; ++c)
-                            tma_load_1d(dst + c * (TT + 1) * H + k_lo, xg + (size_t)c * L + s0 + k_lo,
-                                        (uint32_t)((k_hi - k_lo) * sizeof(float)), &samp_full[s]);
-                    } else {
-                        mbar_arrive(&samp_full[s]);
-                    }
+                        tma_load_1d(dst + c * (TT + 1) * H + k_lo, xg + (size_t)c * L + s0 + k_lo,
+                                    (uint32_t)((k_hi - k_lo) * sizeof(float)), &samp_full[s]);
+                } else {
+                    mbar_arrive(&samp_full[s]);
                 }
             }
         };
-        if (SCM) acc_reset();
+        // Nyquist bin: the spectrum is real there, so an SCM entry is a plain product y_i y_j.
+        // lane l <-> (frame l / C, channel l % C) for the un-mixing and the Y store,
+        // lane p <-> channel pair p (and p + 32 when C = 8) for the accumulation.
+        constexpr int NP = C * (C + 1) / 2;
+        constexpr int NSLOT = NP > 32 ? 2 : 1;
+        int pi[NSLOT], pj[NSLOT], row[NSLOT];
+#pragma unroll
+        for (int u = 0; u < NSLOT; ++u) {
+            const int pp = min(lane + 32 * u, NP - 1);
+            if (pp < C) {
+                pi[u] = pj[u] = pp;
+                row[u] = pp;
+            } else {
+                int o = pp - C, i = 0, n = C - 1;
+                while (o >= n) {
+                    o -= n;
+                    --n;
+                    ++i;
+                }
+                pi[u] = i;
+                pj[u] = i + 1 + o;
+                row[u] = C + 2 * (pp - C);
+            }
+        }
+        float as[NMX][NSLOT], an[NMX][NSLOT];
+        auto nyq_reset = [&]() {
+#pragma unroll
+            for (int q = 0; q < NMX; ++q)
+#pragma unroll
+                for (int u = 0; u < NSLOT; ++u) as[q][u] = an[q][u] = 0.f;
+        };
+        nyq_reset();
         load_tile(0);
         for (int it = 0; it < n_it; ++it) {
             if (it + 1 < n_it) load_tile(it + 1);
-            const long long i = lo + it;
-            const int grp = (int)(i / tiles_per_grp), t0 = (int)(i % tiles_per_grp) * TT;
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
-            // Nyquist bin: lane tl <-> frame t0 + tl
-            float m = 0.f;
-            if (SCM && lane < nfr)
-                m = p.mask_ft ? p.mask[((size_t)grp * F + (F - 1)) * T + t0 + lane]
-                              : p.mask[((size_t)grp * T + t0 + lane) * F + (F - 1)];
-            mbar_wait(&spec_full[s], (it >> 1) & 1);
-            if (lane < nfr) {
-                float2 y[C];
-                unmix(spec + s * G::SPEC, lane, N / 2, y);
+            float mq[NMX];
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    if (c < c_valid) p.Y[(((size_t)grp * C + c) * T + t0 + lane) * F + (F - 1)] = y[c];
-                if (SCM) acc_step(y, m);
+            for (int q = 0; q < NMX; ++q) mq[q] = (SCM && lane < nfr) ? mask_at(q, grp, t0 + lane, F - 1) : 0.f;
+            mbar_wait(&spec_full[s], (it >> 1) & 1);
+#pragma unroll
+            for (int r = lane; r < TT * C; r += 32) {
+                const int tl_l = r / C, c_l = r % C;
+                float yv = 0.f;
+                if (tl_l < nfr && c_l < c_valid) {
+                    const float2 z = spec[s * G::SPEC + (size_t)(tl_l * P + c_l / 2) * ROWP + N / 2];
+                    yv = (c_l & 1) ? z.y + z.y : z.x + z.x;
+                    p.Y[(((size_t)grp * C + c_l) * T + t0 + tl_l) * F + (F - 1)] = make_float2(yv, 0.f);
+                }
+                nyq[r] = yv;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&spec_empty[s]);
-            const bool seg_end = (it + 1 == n_it) || ((i + 1) % tiles_per_grp == 0);
-            if (SCM && seg_end) {
-                // reduce the per-frame lanes (fixed butterfly order), lane 0 writes bin N/2
+            if (SCM) {
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
+                for (int tl = 0; tl < TT; ++tl) {
+                    if (tl < nfr) {   // warp-uniform
+                        float pr[NSLOT];
 #pragma unroll
-                    for (int q = 0; q < C; ++q) {
-                        ps_d[q] += __shfl_xor_sync(0xffffffffu, ps_d[q], off);
-                        pn_d[q] += __shfl_xor_sync(0xffffffffu, pn_d[q], off);
-                    }
+                        for (int u = 0; u < NSLOT; ++u)
+                            pr[u] = nyq[tl * C + pi[u]] * nyq[tl * C + pj[u]];
 #pragma unroll
-                    for (int q = 0; q < NOFF; ++q) {
-                        ps_o[q].x += __shfl_xor_sync(0xffffffffu, ps_o[q].x, off);
-                        ps_o[q].y += __shfl_xor_sync(0xffffffffu, ps_o[q].y, off);
-                        pn_o[q].x += __shfl_xor_sync(0xffffffffu, pn_o[q].x, off);
-                        pn_o[q].y += __shfl_xor_sync(0xffffffffu, pn_o[q].y, off);
+                        for (int q = 0; q < NM; ++q) {
+                            const float m = __shfl_sync(0xffffffffu, mq[q], tl), om = 1.f - m;
+                            const float a = m * m, b = om * om;
+#pragma unroll
+                            for (int u = 0; u < NSLOT; ++u) {
+                                as[q][u] = fmaf(a, pr[u], as[q][u]);
+                                an[q][u] = fmaf(b, pr[u], an[q][u]);
+                            }
+                        }
                     }
                 }
-                if (lane == 0) acc_flush(grp, F - 1);
-                acc_reset();
-            }
-        }
-    } else if (warp <= G::FFT_WARPS) {
-        // =========================================================== FFT warps
-        const int w = warp - 1;
-        float win[RA];   // window for n = lane + 32 j (pre-scaled by 1/2 for the two-for-one split)
+                const bool seg_end = (it + 1 == n_it) || ((lo + it + 1) % tiles_per_grp == 0);
+                if (seg_end) {
+                    float* out = p.part + ((size_t)grp * p.slots_per_grp + seg_slot(grp)) * NACC * F + (F - 1);
 #pragma unroll
-        for (int j = 0; j < RA; ++j) win[j] = p.window[lane + 32 * j];
+                    for (int u = 0; u < NSLOT; ++u) {
+                        const int pp = lane + 32 * u;
+                        if (pp < NP) {
+#pragma unroll
+                            for (int q = 0; q < NM; ++q) {
+                                float* os = out + (size_t)(q * 2 * C * C) * F;
+                                float* on = os + (size_t)(C * C) * F;
+                                os[(size_t)row[u] * F] = as[q][u];
+                                on[(size_t)row[u] * F] = an[q][u];
+                                if (pp >= C) {
+                                    os[(size_t)(row[u] + 1) * F] = 0.f;
+                                    on[(size_t)(row[u] + 1) * F] = 0.f;
+                                }
+                            }
+                        }
+                    }
+                    nyq_reset();
+                }
+            }
+            __syncwarp();   // nyq[] is rewritten by the next tile
+        }
+    } else if (warp < G::LEAD_WARPS + G::FFT_WARPS) {
+        if (G::REALLOC) set_maxnreg_inc<G::REG_FFT>();
+        // =========================================================== FFT warps
+        const int w = warp - G::LEAD_WARPS;
+        constexpr bool WINREG = (RA <= 16);
+        float win[WINREG ? RA : 1];   // window for n = lane + 32 j (pre-scaled by 1/2 for the two-for-one split)
+        if (WINREG) {
+#pragma unroll
+            for (int j = 0; j < RA; ++j) win[j] = p.window[lane + 32 * j];
+        }
         for (int it = 0; it < n_it; ++it) {
-            const long long i = lo + it;
-            const int grp = (int)(i / tiles_per_grp), t0 = (int)(i % tiles_per_grp) * TT;
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
             const uint32_t ph = (it >> 1) & 1;
             const float* sm = samp + s * SAMP;
-            float2* job = spec + s * G::SPEC + (size_t)w * NB * ROWP;
             mbar_wait(&samp_full[s], ph);
             {
                 const int s0 = t0 * H - H;
-                const bool interior = p.use_tma && nfr == TT && s0 >= 0 && s0 + (TT + 1) * H <= L;
-                if (!interior) {   // CTA-uniform: cooperative scalar fill by the 8 FFT warps
+                const int cnt = (nfr + 1) * H;
+                int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);   // [k_lo, k_hi) arrived by TMA
+                if (!p.use_tma || k_hi <= k_lo) k_lo = k_hi = 0;
+                const int n_fill = cnt - (k_hi - k_lo);
+                if (n_fill > 0) {   // CTA-uniform: cooperative scalar fill (reflect padding) by the FFT warps
                     const float* xg = p.x + (size_t)grp * C * L;
                     float* dst = samp + s * SAMP;
-                    const int cnt = (nfr + 1) * H;
-                    int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);   // [k_lo, k_hi) arrived by TMA
-                    if (!p.use_tma || k_hi <= k_lo) k_lo = k_hi = 0;
-                    const int n_fill = cnt - (k_hi - k_lo);
                     named_bar_sync(1, 32 * G::FFT_WARPS);     // every FFT warp is done with this stage
                     for (int c = 0; c < c_valid; ++c)
 #pragma unroll 4
@@ -291,158 +392,184 @@ __global__ void __launch_bounds__(FftGeom<N>::THREADS, 1) stft_scm_kernel(StftAr
                 }
             }
             mbar_wait(&spec_empty[s], ph ^ 1);                // spectrum stage s free (tile it-2 consumed)
-            // inter-pass twiddles W_N^(lane k1): fetched once per job, ahead of the butterflies
-            constexpr bool TWREG = (RA <= 16);
-            float2 twr[TWREG ? RA : 1];
-            if (TWREG) {
+            const bool full = (nfr == TT && c_valid == C && (C % 2 == 0) && (G::ITEMS % P == 0));
+#pragma unroll 1
+            for (int jj = 0; jj < G::JPW; ++jj) {
+                const int jb = w * G::JPW + jj;
+                float2* job = spec + s * G::SPEC + (size_t)jb * NB * ROWP;
+                // inter-pass twiddles W_N^(lane k1): fetched once per job, shared by its transforms
+                constexpr bool TWREG = (RA <= 16);
+                float2 twr[TWREG ? RA : 1];
+                if (TWREG) {
 #pragma unroll
-                for (int k1 = 1; k1 < RA; ++k1) twr[k1] = tw[k1 * 32 + lane];
-            }
-            const bool full = (nfr == TT && c_valid == C && (C % 2 == 0));
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int item = w * NB + q;
-                const int tl = item / P, pr = item % P;
-                const int ca = 2 * pr, cb = 2 * pr + 1;
-                const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
-                const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
-                float2 v[RA];
-                if (full || (tl < nfr && cb < c_valid)) {
-#pragma unroll
-                    for (int j = 0; j < RA; ++j) v[j] = make_float2(xa[32 * j] * win[j], xb[32 * j] * win[j]);
-                } else if (tl < nfr && ca < c_valid) {
-#pragma unroll
-                    for (int j = 0; j < RA; ++j) v[j] = make_float2(xa[32 * j] * win[j], 0.f);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < RA; ++j) v[j] = make_float2(0.f, 0.f);
+                    for (int k1 = 1; k1 < RA; ++k1) twr[k1] = tw[k1 * 32 + lane];
                 }
-                if (q == NB - 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&samp_empty[s]);   // all samples of this job are in registers
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int item = jb * NB + q;
+                    const int tl = item / P, pr = item % P;
+                    const int ca = 2 * pr, cb = 2 * pr + 1;
+                    const float* xa = sm + ca * (TT + 1) * H + tl * H + lane;
+                    const float* xb = sm + cb * (TT + 1) * H + tl * H + lane;
+                    float2 v[RA];
+                    if (full || (tl < nfr && cb < c_valid)) {
+#pragma unroll
+                        for (int j = 0; j < RA; ++j) {
+                            const float wj = WINREG ? win[j] : p.window[lane + 32 * j];
+                            v[j] = __fmul2_rn(make_float2(xa[32 * j], xb[32 * j]), make_float2(wj, wj));
+                        }
+                    } else if (tl < nfr && ca < c_valid) {
+#pragma unroll
+                        for (int j = 0; j < RA; ++j) {
+                            const float wj = WINREG ? win[j] : p.window[lane + 32 * j];
+                            v[j] = make_float2(xa[32 * j] * wj, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < RA; ++j) v[j] = make_float2(0.f, 0.f);
+                    }
+                    if (jj == G::JPW - 1 && q == NB - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&samp_empty[s]);   // all samples of this warp are in registers
+                    }
+                    dft_reg<RA, false>(v);
+#pragma unroll
+                    for (int k1 = 1; k1 < RA; ++k1) v[k1] = cmul(v[k1], TWREG ? twr[k1] : tw[k1 * 32 + lane]);
+#pragma unroll
+                    for (int k1 = 0; k1 < RA; ++k1) job[(q * RA + k1) * 33 + lane] = v[k1];   // scratch [32 rows][33]
                 }
-                if (!(p.dbg & 4)) dft_reg<RA, false>(v);
+                __syncwarp();
+                float2 u[32];
 #pragma unroll
-                for (int k1 = 0; k1 < RA; ++k1) {
-                    const float2 val = (k1 == 0) ? v[0] : cmul(v[k1], TWREG ? twr[k1] : tw[k1 * 32 + lane]);
-                    job[(q * RA + k1) * 33 + lane] = val;      // scratch [32 rows][33]: conflict-free both ways
+                for (int l = 0; l < 32; ++l) u[l] = job[lane * 33 + l];
+                __syncwarp();
+                dft_reg<32, false>(u);
+                {
+                    float2* row = job + (lane / RA) * ROWP + (lane % RA);
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; ++k2) row[RA * k2] = u[k2];
                 }
-            }
-            __syncwarp();
-            float2 u[32];
-#pragma unroll
-            for (int l = 0; l < 32; ++l) u[l] = job[lane * 33 + l];
-            __syncwarp();
-            if (!(p.dbg & 4)) dft_reg<32, false>(u);
-            {
-                float2* row = job + (lane / RA) * ROWP + (lane % RA);
-#pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) row[RA * k2] = u[k2];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&spec_full[s]);
         }
     } else {
+        if (G::REALLOC) set_maxnreg_inc<G::REG_SCM>();
         // =========================================================== SCM warps: thread <-> bin f
-        const int f = (warp - 1 - G::FFT_WARPS) * 32 + lane;   // 0 .. N/2 - 1
-        float mk[TT];
-        auto load_mask = [&](int it) {
-            const long long i = lo + it;
-            const int grp = (int)(i / tiles_per_grp), t0 = (int)(i % tiles_per_grp) * TT;
-            const int nfr = min(TT, T - t0);
+        const int f = (warp - G::LEAD_WARPS - G::FFT_WARPS) * 32 + lane;   // 0 .. N/2 - 1
+        const int fn = (N - f) & (N - 1);
+        ScmAcc<C, NM> acc;
+        float mk[NMX][MC];
+        // masks of chunk `ch` of tile `it` (a chunk past the CTA's last tile loads nothing)
+        auto load_mask = [&](int it, int ch) {
+            if (it >= n_it) return;
+            int grp, t0;
+            tile_of(it, grp, t0);
 #pragma unroll
-            for (int tl = 0; tl < TT; ++tl) {
-                mk[tl] = 0.f;
-                if (tl < nfr)
-                    mk[tl] = p.mask_ft ? p.mask[((size_t)grp * F + f) * T + t0 + tl]
-                                       : p.mask[((size_t)grp * T + t0 + tl) * F + f];
-            }
+            for (int q = 0; q < NM; ++q)
+#pragma unroll
+                for (int i = 0; i < MC; ++i) {
+                    const int t = t0 + ch * MC + i;
+                    mk[q][i] = (ch * MC + i < TT && t < T) ? mask_at(q, grp, t, f) : 0.f;
+                }
         };
         if (SCM) {
-            acc_reset();
-            load_mask(0);
+            acc.reset();
+            load_mask(0, 0);
         }
         for (int it = 0; it < n_it; ++it) {
-            const long long i = lo + it;
-            const int grp = (int)(i / tiles_per_grp), t0 = (int)(i % tiles_per_grp) * TT;
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
-            float mcur[TT];
-#pragma unroll
-            for (int tl = 0; tl < TT; ++tl) mcur[tl] = SCM ? mk[tl] : 0.f;
-            if (SCM && it + 1 < n_it) load_mask(it + 1);          // in flight while this tile is processed
-            mbar_wait(&spec_full[s], (it >> 1) & 1);
             const float2* stage = spec + s * G::SPEC;
-            float2* yc[C];   // per-channel output rows: frame offsets below are compile-time immediates
+            float2* ybase = p.Y + ((size_t)grp * C * T + t0) * F + f;
+            const size_t cstride = (size_t)T * F;
+            const bool full = (nfr == TT && c_valid == C);
 #pragma unroll
-            for (int c = 0; c < C; ++c) yc[c] = p.Y + (((size_t)grp * C + c) * T + t0) * F + f;
-            if (nfr == TT && c_valid == C) {                     // full tile: straight-line code
+            for (int ch = 0; ch < NCH; ++ch) {
+                float mcur[NMX][MC];
 #pragma unroll
-                for (int tl = 0; tl < TT; ++tl) {
-                    float2 y[C];
-                    unmix(stage, tl, f, y);
-                    if (!(p.dbg & 1)) {
+                for (int q = 0; q < NMX; ++q)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) __stcs(&yc[c][tl * F], y[c]);
-                    }
-                    if (SCM && !(p.dbg & 2)) acc_step(y, mcur[tl]);
+                    for (int i = 0; i < MC; ++i) mcur[q][i] = SCM ? mk[q][i] : 0.f;
+                if (SCM) {   // next chunk's masks: in flight while this chunk is processed
+                    if (ch + 1 < NCH)
+                        load_mask(it, ch + 1);
+                    else
+                        load_mask(it + 1, 0);
                 }
-            } else {
+                if (ch == 0) mbar_wait(&spec_full[s], (it >> 1) & 1);
 #pragma unroll
-                for (int tl = 0; tl < TT; ++tl) {
-                    if (tl < nfr) {
+                for (int i = 0; i < MC; ++i) {
+                    const int tl = ch * MC + i;
+                    if (tl < TT && (full || tl < nfr)) {
+                        // un-mix the two-for-one spectra (window carries the 1/2):
+                        //   A = Z[f] + conj(Z[N-f]),  B = -i (Z[f] - conj(Z[N-f]))
                         float2 y[C];
-                        unmix(stage, tl, f, y);
+#pragma unroll
+                        for (int pr = 0; pr < P; ++pr) {
+                            const float2* row = stage + (size_t)(tl * P + pr) * ROWP;
+                            const float2 zf = row[f], zn = row[fn];
+                            y[2 * pr] = __fadd2_rn(zf, make_float2(zn.x, -zn.y));
+                            if (2 * pr + 1 < C) y[2 * pr + 1] = __fadd2_rn(make_float2(zf.y, -zf.x), make_float2(zn.y, zn.x));
+                        }
 #pragma unroll
                         for (int c = 0; c < C; ++c)
-                            if (c < c_valid) yc[c][tl * F] = y[c];
-                        if (SCM) acc_step(y, mcur[tl]);
+                            if (full || c < c_valid) __stcs(ybase + c * cstride + tl * F, y[c]);
+                        if (SCM) {
+                            float m[NMX];
+#pragma unroll
+                            for (int q = 0; q < NMX; ++q) m[q] = mcur[q][i];
+                            acc.step(y, m);
+                        }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&spec_empty[s]);
-            const bool seg_end = (it + 1 == n_it) || ((i + 1) % tiles_per_grp == 0);
+            const bool seg_end = (it + 1 == n_it) || ((lo + it + 1) % tiles_per_grp == 0);
             if (SCM && seg_end) {
-                acc_flush(grp, f);
-                acc_reset();
+                acc.flush(p.part + ((size_t)grp * p.slots_per_grp + seg_slot(grp)) * NACC * F + f, F);
+                acc.reset();
             }
         }
     }
 }
 
-// Reduce the (group, CTA) segment partials in fixed slot order, scale by 1/T, expand to full Hermitian
-// matrices Rss, Rnn [n_grp][F][C][C] complex64 (R[i][j] = mean_t a_i conj(a_j), np.outer convention).
-// One block per group, one thread per bin: all 2 C^2 * n_slot loads of a thread are independent
-// (coalesced over bins), so the kernel costs about one memory round trip.
+// Reduce the (group, CTA) segment partials of mask set `set` in fixed slot order, scale by 1/T, expand
+// to full Hermitian matrices Rss, Rnn [n_grp][F][C][C] complex64 (R[i][j] = mean_t a_i conj(a_j),
+// np.outer convention).  One block per group, one thread per bin: the loads of a thread are
+// independent (coalesced over bins), so the kernel costs about one memory round trip.
 template <int C>
 __global__ void __launch_bounds__(288) scm_finalize_kernel(const float* __restrict__ part, float2* __restrict__ Rss,
                                                            float2* __restrict__ Rnn, int n_grp, int slots_per_grp,
-                                                           int tiles_per_grp, int n_cta, int F, float inv_T) {
-    constexpr int NACC = 2 * C * C;
+                                                           int tiles_per_grp, int n_cta, int F, float inv_T, int n_set,
+                                                           int set) {
+    constexpr int NA = 2 * C * C;
     const int g = blockIdx.x;
     const long long total = (long long)n_grp * tiles_per_grp;
     const int b_first = cta_of_tile((long long)g * tiles_per_grp, total, n_cta);
     const int n_slot = cta_of_tile((long long)(g + 1) * tiles_per_grp - 1, total, n_cta) - b_first + 1;
+    const size_t slot_stride = (size_t)n_set * NA * F;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        const float* base = part + (size_t)g * slots_per_grp * NACC * F + f;
-        float acc[NACC];
-#pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-        for (int sl = 0; sl < n_slot; ++sl) {
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) acc[a] += __ldg(base + ((size_t)sl * NACC + a) * F);
-        }
-#pragma unroll
+        const float* base = part + (size_t)g * slots_per_grp * slot_stride + (size_t)set * NA * F + f;
+#pragma unroll 1
         for (int which = 0; which < 2; ++which) {
+            float acc[C * C];
+#pragma unroll
+            for (int a = 0; a < C * C; ++a) acc[a] = 0.f;
+            for (int sl = 0; sl < n_slot; ++sl) {
+#pragma unroll
+                for (int a = 0; a < C * C; ++a) acc[a] += __ldg(base + sl * slot_stride + (size_t)(which * C * C + a) * F);
+            }
             float2* R = (which == 0 ? Rss : Rnn) + ((size_t)g * F + f) * C * C;
-            const float* q = acc + which * C * C;
             int o = 0;
 #pragma unroll
             for (int i = 0; i < C; ++i) {
-                R[i * C + i] = make_float2(q[i] * inv_T, 0.f);
+                R[i * C + i] = make_float2(acc[i] * inv_T, 0.f);
 #pragma unroll
                 for (int j = i + 1; j < C; ++j) {
-                    const float re = q[C + 2 * o] * inv_T, im = q[C + 2 * o + 1] * inv_T;
+                    const float re = acc[C + 2 * o] * inv_T, im = acc[C + 2 * o + 1] * inv_T;
                     R[i * C + j] = make_float2(re, im);
                     R[j * C + i] = make_float2(re, -im);
                     ++o;
@@ -453,18 +580,9 @@ __global__ void __launch_bounds__(288) scm_finalize_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------ host side
-template <int N>
-static int tiles_per_grp_n(int C, int T) {
-    const int tt = tile_frames_n<N>(C);
-    return (T + tt - 1) / tt;
-}
-
 int stft_tiles_per_grp(int n_fft, int C, int T) {
-    switch (n_fft) {
-        case 256: return tiles_per_grp_n<256>(C, T);
-        case 512: return tiles_per_grp_n<512>(C, T);
-        default: return tiles_per_grp_n<1024>(C, T);
-    }
+    const int tt = stft_tile_frames(n_fft, C);
+    return (T + tt - 1) / tt;
 }
 
 // Upper bound on the number of CTAs whose tile range intersects one group.
@@ -475,47 +593,92 @@ int stft_slots_per_grp(int n_grp, int tiles_per_grp, int n_cta) {
     return (int)(tiles_per_grp / min_range) + 2;
 }
 
-template <int N, int C, bool SCM>
+bool stft_scm_supported(int n_fft, int C, int n_mask) {
+    if (C < 1 || C > 8 || n_mask < 0 || n_mask > 2) return false;
+    if (n_fft != 256 && n_fft != 512 && n_fft != 1024) return false;
+    if (C > 4 && (n_mask == 2 || n_fft == 1024)) return false;   // 128 accumulators per bin are the register limit
+    if (n_mask == 2 && n_fft == 1024) return false;
+    return true;
+}
+
+template <int N, int C, int NM>
 static cudaError_t launch_one(const StftArgs& a, int n_cta, cudaStream_t st) {
-    using G = FftGeom<N>;
-    auto kern = stft_scm_kernel<N, C, SCM>;
-    const size_t smem = smem_bytes<N>(C);
+    using G = StftCfg<N, C>;
+    auto kern = stft_scm_kernel<N, C, NM>;
+    const size_t smem = smem_bytes<N, C>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (G::REALLOC) {   // setmaxnreg.inc would wait forever if the launch allocation were smaller than the budgets
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        if ((long long)fa.numRegs * G::THREADS < G::REG_SUM) return cudaErrorLaunchOutOfResources;
+    }
     kern<<<n_cta, G::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-template <int N, bool SCM>
-static cudaError_t launch_c(const StftArgs& a, int C, int n_cta, cudaStream_t st) {
-    switch (C) {
-        case 1: return launch_one<N, 1, SCM>(a, n_cta, st);
-        case 2: return launch_one<N, 2, SCM>(a, n_cta, st);
-        case 3: return launch_one<N, 3, SCM>(a, n_cta, st);
-        case 4: return launch_one<N, 4, SCM>(a, n_cta, st);
-        default: return cudaErrorInvalidValue;
+template <int N, int C>
+static cudaError_t launch_nm(const StftArgs& a, int nm, int n_cta, cudaStream_t st) {
+    if (nm == 0) return launch_one<N, C, 0>(a, n_cta, st);
+    if (nm == 1) return launch_one<N, C, 1>(a, n_cta, st);
+    if constexpr (C <= 4 && N <= 512) {
+        if (nm == 2) return launch_one<N, C, 2>(a, n_cta, st);
     }
+    return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, bool scm, cudaStream_t st) {
+template <int N>
+static cudaError_t launch_c(const StftArgs& a, int C, int nm, int n_cta, cudaStream_t st) {
+    switch (C) {
+        case 1: return launch_nm<N, 1>(a, nm, n_cta, st);
+        case 2: return launch_nm<N, 2>(a, nm, n_cta, st);
+        case 3: return launch_nm<N, 3>(a, nm, n_cta, st);
+        case 4: return launch_nm<N, 4>(a, nm, n_cta, st);
+        default: break;
+    }
+    if constexpr (N <= 512) {
+        switch (C) {
+            case 5: return launch_nm<N, 5>(a, nm, n_cta, st);
+            case 6: return launch_nm<N, 6>(a, nm, n_cta, st);
+            case 7: return launch_nm<N, 7>(a, nm, n_cta, st);
+            case 8: return launch_nm<N, 8>(a, nm, n_cta, st);
+            default: break;
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_stft_scm(const StftArgs& a, int n_fft, int C, int n_cta, int n_mask, cudaStream_t st) {
+    if (!stft_scm_supported(n_fft, C, n_mask)) return cudaErrorInvalidValue;
     switch (n_fft) {
-        case 256: return scm ? launch_c<256, true>(a, C, n_cta, st) : launch_c<256, false>(a, C, n_cta, st);
-        case 512: return scm ? launch_c<512, true>(a, C, n_cta, st) : launch_c<512, false>(a, C, n_cta, st);
-        case 1024: return scm ? launch_c<1024, true>(a, C, n_cta, st) : launch_c<1024, false>(a, C, n_cta, st);
+        case 256: return launch_c<256>(a, C, n_mask, n_cta, st);
+        case 512: return launch_c<512>(a, C, n_mask, n_cta, st);
+        case 1024: return launch_c<1024>(a, C, n_mask, n_cta, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t launch_scm_finalize(const float* part, float2* Rss, float2* Rnn, int n_grp, int slots_per_grp,
-                                int tiles_per_grp, int n_cta, int C, int F, int T, cudaStream_t st) {
+                                int tiles_per_grp, int n_cta, int C, int F, int T, int n_set, int set, cudaStream_t st) {
     const float inv_T = 1.0f / (float)T;
+#define DISCO_FIN(CC)                                                                                              \
+    case CC:                                                                                                       \
+        scm_finalize_kernel<CC><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, \
+                                                       F, inv_T, n_set, set);                                      \
+        break;
     switch (C) {
-        case 1: scm_finalize_kernel<1><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
-        case 2: scm_finalize_kernel<2><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
-        case 3: scm_finalize_kernel<3><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
-        case 4: scm_finalize_kernel<4><<<n_grp, 288, 0, st>>>(part, Rss, Rnn, n_grp, slots_per_grp, tiles_per_grp, n_cta, F, inv_T); break;
+        DISCO_FIN(1)
+        DISCO_FIN(2)
+        DISCO_FIN(3)
+        DISCO_FIN(4)
+        DISCO_FIN(5)
+        DISCO_FIN(6)
+        DISCO_FIN(7)
+        DISCO_FIN(8)
         default: return cudaErrorInvalidValue;
     }
+#undef DISCO_FIN
     return cudaGetLastError();
 }
 

@@ -25,7 +25,35 @@ def _layout(layout):
 
 
 def _stream():
+    """Current stream of the CURRENT device; every public op below runs under the device of its operands
+    (see `_on_device`), so this is the stream of the tensors' device."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """Run an op with the device of its tensor operands current: the library keeps per-device tables
+    (cudaGetDevice) and launches on the current stream, so operands on another device than the current one
+    would otherwise be dereferenced by kernels running on the wrong GPU.  Mixed devices are rejected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        stack = list(args) + list(kw.values())
+        while stack:
+            a = stack.pop()
+            if isinstance(a, (tuple, list)):
+                stack.extend(a)
+            elif isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise ValueError("%s: operands live on different devices (%s, %s)" % (fn.__name__, dev, a.device))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _ptr(t):
@@ -52,6 +80,7 @@ def init(n_fft=512):
     _lib.check(_lib.load().disco_init(int(n_fft)))
 
 
+@_on_device
 def stft(x, n_fft=512):
     """x [..., L] float32 -> Y [..., T, F] complex64 (librosa center/reflect/periodic-Hann semantics)."""
     _need(x, torch.float32, "x")
@@ -63,6 +92,7 @@ def stft(x, n_fft=512):
     return Y
 
 
+@_on_device
 def stft_scm(x, mask, n_fft=512, mask_layout="TF", keep_partials=False):
     """Fused STFT + masked SCM.  x [G, C, L] float32, mask [G, T, F] (or [G, F, T]) float32
     -> Y [G, C, T, F] complex64, Rss, Rnn [G, F, C, C] complex64.
@@ -79,6 +109,8 @@ def stft_scm(x, mask, n_fft=512, mask_layout="TF", keep_partials=False):
     if tuple(mask.shape) != want:
         raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
     lib = _lib.load()
+    if not lib.disco_stft_scm_supported(n_fft, C, 1):
+        raise NotImplementedError("fused STFT+SCM: %d channels at n_fft=%d (use stft + masked_scm)" % (C, n_fft))
     Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
     ws_bytes = lib.disco_stft_scm_workspace(G, C, L, n_fft)
     ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
@@ -93,6 +125,7 @@ def stft_scm(x, mask, n_fft=512, mask_layout="TF", keep_partials=False):
     return Y, Rss, Rnn
 
 
+@_on_device
 def mwf_solve_workspace(ws, G, C, L, n_fft=512, mu=1.0, type="gevd", rank=1, want_scm=False):
     """mwf_solve on the SCMs a preceding stft_scm(..., keep_partials=True) left in `ws`.
     Returns W, t1 [G, F, C] (and Rss, Rnn [G, F, C, C] when want_scm)."""
@@ -111,6 +144,88 @@ def mwf_solve_workspace(ws, G, C, L, n_fft=512, mu=1.0, type="gevd", rank=1, wan
     return (W, T1, Rss, Rnn) if want_scm else (W, T1)
 
 
+def stft_scm_supported(n_fft, C, n_mask=1):
+    """Whether the fused STFT+SCM kernel covers (n_fft, channels per group, number of masks)."""
+    return bool(_lib.load().disco_stft_scm_supported(int(n_fft), int(C), int(n_mask)))
+
+
+@_on_device
+def stft_scm2(x, mask_a, mask_b, n_fft=512, mask_layout="TF"):
+    """Fused STFT + the masked SCMs under TWO masks in one pass (single-node arrays: step-1 and step-2
+    statistics are taken over the same Y, reference tango.py:357-364 and :431-440 with K = 1).
+    x [G, C, L], masks [G, T, F] (or [G, F, T]) -> Y [G, C, T, F], workspace (partial sums of both sets,
+    consumed by mwf_solve_workspace2 / scm_from_workspace)."""
+    _need(x, torch.float32, "x")
+    _need(mask_a, torch.float32, "mask_a")
+    _need(mask_b, torch.float32, "mask_b")
+    if x.dim() != 3:
+        raise ValueError("x must be [groups, channels, samples]")
+    G, C, L = x.shape
+    T, F = n_frames(L, n_fft), n_fft // 2 + 1
+    lay = _layout(mask_layout)
+    want = (G, T, F) if lay == TF else (G, F, T)
+    if tuple(mask_a.shape) != want or tuple(mask_b.shape) != want:
+        raise ValueError("mask shapes %s / %s, expected %s" % (tuple(mask_a.shape), tuple(mask_b.shape), want))
+    lib = _lib.load()
+    if not lib.disco_stft_scm_supported(n_fft, C, 2):
+        raise NotImplementedError("two-mask fused STFT+SCM: %d channels at n_fft=%d" % (C, n_fft))
+    Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
+    ws_bytes = lib.disco_stft_scm2_workspace(G, C, L, n_fft)
+    ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
+    _lib.check(lib.disco_stft_scm2(_ptr(x), _ptr(mask_a), _ptr(mask_b), lay, _ptr(Y), G, C, L, n_fft, _ptr(ws),
+                                   ws_bytes, _stream()))
+    return Y, ws
+
+
+@_on_device
+def scm_from_workspace(ws, G, C, L, n_fft=512, n_set=1, set=0):
+    """Rss, Rnn [G, F, C, C] of mask set `set` from the partial sums a fused STFT+SCM call left in `ws`."""
+    F = n_fft // 2 + 1
+    Rss = torch.empty((G, F, C, C), dtype=torch.complex64, device=ws.device)
+    Rnn = torch.empty_like(Rss)
+    _lib.check(_lib.load().disco_scm_from_workspace(_ptr(ws), int(n_set), int(set), _ptr(Rss), _ptr(Rnn), G, C, L,
+                                                    n_fft, _stream()))
+    return Rss, Rnn
+
+
+@_on_device
+def mwf_solve_workspace2(ws, G, C, L, n_fft=512, mu=1.0, type="gevd", rank=1):
+    """Both filter sets of a stft_scm2 workspace in one launch: W, t1 [2, G, F, C] (0: mask_a, 1: mask_b)."""
+    if type not in FILTER_TYPES:
+        raise AttributeError("Unknown filter reference")
+    F = n_fft // 2 + 1
+    r = 0 if rank in ("full", "Full", None) else int(rank)
+    W = torch.empty((2, G, F, C), dtype=torch.complex64, device=ws.device)
+    T1 = torch.empty_like(W)
+    _lib.check(_lib.load().disco_mwf_solve_workspace2(_ptr(ws), _ptr(W), _ptr(T1), G, C, L, n_fft,
+                                                      FILTER_TYPES[type], r, float(mu), _stream()))
+    return W, T1
+
+
+@_on_device
+def filter_dual(W1, W2, Y, ref=0, n_fft=512, out_layout="TF", want_zn=True):
+    """Single-node groups: z = w1^H y, zn = y[ref] - z and yf = w2^H y in ONE pass over Y (reference
+    tango.py:369-376 and :445-450 with K = 1).  W1, W2 [..., F, C], Y [..., C, T, F] -> z, zn, yf
+    [..., T, F] (or [..., F, T])."""
+    _need(W1, torch.complex64, "W1")
+    _need(W2, torch.complex64, "W2")
+    _need(Y, torch.complex64, "Y")
+    C, T, F = Y.shape[-3:]
+    lead = tuple(Y.shape[:-3])
+    G = Y.numel() // (C * T * F)
+    if tuple(W1.shape) != lead + (F, C) or tuple(W2.shape) != lead + (F, C):
+        raise ValueError("W1 / W2 shape %s / %s, expected %s" % (tuple(W1.shape), tuple(W2.shape), lead + (F, C)))
+    lay = _layout(out_layout)
+    shape = lead + ((T, F) if lay == TF else (F, T))
+    z = torch.empty(shape, dtype=torch.complex64, device=Y.device)
+    zn = torch.empty_like(z) if want_zn else None
+    yf = torch.empty_like(z)
+    _lib.check(_lib.load().disco_filter_dual(_ptr(W1), _ptr(W2), _ptr(Y), _ptr(z), _ptr(zn), _ptr(yf), int(ref), lay,
+                                             G, C, T, n_fft, _stream()))
+    return z, zn, yf
+
+
+@_on_device
 def tf_mask(S, N, type="irm1", bin_thr=0.0):
     """Oracle mask (reference dnn/utils.py:44-71) on device, float32.  Same shape as S."""
     _need(S, torch.complex64, "S")
@@ -133,6 +248,7 @@ def _sel(node_sel, K):
     return arr, len(node_sel), len(node_sel)
 
 
+@_on_device
 def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
     """Y [B, Ksel, C, T, F], Z [B, K, T, F] or None (K = 1), mask [B, Ksel, T, F] / [B, Ksel, F, T] or None
     -> Rss, Rnn [B, Ksel, F, D, D], D = C + K - 1 (own mics, then z of the other nodes)."""
@@ -164,6 +280,7 @@ def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
     return Rss, Rnn
 
 
+@_on_device
 def filter_sum_scm(W1, Y, mask, ref=0, n_fft=512, mask_layout="TF"):
     """Single-node groups (no exchange): z = w1^H y, zn = y[ref] - z AND the masked SCMs of Y under `mask`
     in one pass over Y.  W1 [..., F, C], Y [..., C, T, F], mask [..., T, F] (or [..., F, T]).
@@ -193,6 +310,7 @@ def tango_mid_supported(C, K):
     return bool(_lib.load().disco_tango_mid_supported(int(C), int(K)))
 
 
+@_on_device
 def tango_mid(W1, Y, mask_w, ref=0, n_fft=512):
     """Multi-node arrays: z, zn of every node AND the step-2 SCMs of every node in one pass over Y.
     W1 [B, K, F, C], Y [B, K, C, T, F], mask_w [B, K, T, F] -> z, zn [B, K, T, F], Rss, Rnn [B, K, F, D, D]."""
@@ -212,6 +330,7 @@ def tango_mid(W1, Y, mask_w, ref=0, n_fft=512):
     return z, zn, Rss, Rnn
 
 
+@_on_device
 def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
     """Batched intern_filter (reference internal_formulas.py:31-81).  Rss, Rnn [..., D, D] complex64
     -> W [..., D], t1 [..., D] complex64.  rank 'full'/'Full'/None -> all eigenpairs."""
@@ -229,6 +348,7 @@ def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
     return W, T1
 
 
+@_on_device
 def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", node_sel=None):
     """out = w^H x (conj=True) or w^T x over the concatenated channels [Y ; z of other nodes].
     W [B, Ksel, F, D]; returns out (and resid = x[ref] - out when ref is given), [B, Ksel, T, F] or [.., F, T]."""
@@ -258,6 +378,7 @@ def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", no
     return (out, resid) if ref is not None else out
 
 
+@_on_device
 def istft(Y, length, n_fft=512):
     """Y [..., T, F] complex64 -> x [..., length] float32 (librosa istft semantics, center=True)."""
     _need(Y, torch.complex64, "Y")
@@ -282,6 +403,7 @@ def _cat_dims(Y, Z, node_sel):
     return B, sel, n_sel, K, C, T, F
 
 
+@_on_device
 def scm_recursive(Y, mask, Z=None, lambda_cor=0.95, block=8, power=2, R0=None, n_fft=512, node_sel=None):
     """Exponentially smoothed SCM pair, R <- lambda R + (1 - lambda) w x x^H per frame (reference
     spatial_correlation_matrix, internal_formulas.py:84-103), sampled after every block of `block` frames.
@@ -311,6 +433,7 @@ def scm_recursive(Y, mask, Z=None, lambda_cor=0.95, block=8, power=2, R0=None, n
     return Rss, Rnn
 
 
+@_on_device
 def filter_sum_blocks(W, Y, Z=None, block=8, lag=1, conj=True, ref=0, n_fft=512, node_sel=None):
     """One filter per block of frames: out[t] = W[t // block - lag]^H x[t] (pass-through of channel `ref` while no
     filter exists yet).  W [B, Ksel, J, F, D] -> out, resid = x[ref] - out, [B, Ksel, T, F]."""
@@ -329,6 +452,7 @@ def filter_sum_blocks(W, Y, Z=None, block=8, lag=1, conj=True, ref=0, n_fft=512,
     return out, resid
 
 
+@_on_device
 def band_stats(x, ba, sel=None):
     """IIR filter bank + statistics of every band's output (reference metrics.py:96-110: lfilter, then np.var of
     the selected samples).  x [..., L] float32 (a time slice of a contiguous tensor is taken in place),
@@ -362,6 +486,7 @@ def band_stats(x, ba, sel=None):
     return stats
 
 
+@_on_device
 def transpose_last2(a):
     """[..., R, C] -> [..., C, R] (contiguous) for complex64 / float32 device tensors."""
     R, Cc = a.shape[-2:]
@@ -377,6 +502,7 @@ def transpose_last2(a):
     return out
 
 
+@_on_device
 def apply_mask(X, m, one_minus=False):
     """m * X or (1 - m) * X elementwise (same shapes), complex64 x float32."""
     _need(X, torch.complex64, "X")

@@ -64,7 +64,8 @@ def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mi
     apply_filter=False leaves z_y / zn to a fused later pass (single-node arrays)."""
     B, K, C, L = y.shape
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
-    if oracle_sn is None and C <= 4:
+    fused = oracle_sn is None and ops.stft_scm_supported(n_fft, C, 1)
+    if fused and C <= 4:
         # fused STFT + SCM; the solve reads the per-segment partial sums directly (no finalize launch)
         Y, ws = ops.stft_scm(y.view(B * K, C, L), mask_z.view(B * K, T, F), n_fft, keep_partials=True)
         Y = Y.view(B, K, C, T, F)
@@ -74,6 +75,10 @@ def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mi
         if apply_filter:
             z_y, zn = ops.filter_sum(W1, Y, None, conj=True, ref=ref_mic, n_fft=n_fft)
         return {"Y": Y, "z_y": z_y, "zn": zn, "W1": W1, "R_ss": None, "R_nn": None}
+    elif fused:
+        # 5..8 microphones: same single pass, matrices materialised for the cooperative solver
+        Y, Rss, Rnn = ops.stft_scm(y.view(B * K, C, L), mask_z.view(B * K, T, F), n_fft)
+        Y, Rss, Rnn = Y.view(B, K, C, T, F), Rss.view(B, K, F, C, C), Rnn.view(B, K, F, C, C)
     else:
         Y = ops.stft(y, n_fft)
         if oracle_sn is None:
@@ -124,6 +129,8 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     if oracle and (s is None or n is None):
         raise ValueError("either masks or the clean components (s, n) are required")
     have_sn = s is not None and n is not None
+    if not have_sn and mask_for_z in ("compressed", "use_oracle_refs", "use_oracle_zs"):
+        raise ValueError("mask_for_z=%r needs the clean components s and n" % mask_for_z)
     S = N = None
     if have_sn and (oracle or diagnostics or "use_oracle_" in mask_for_z):
         S, N = ops.stft(s, n_fft), ops.stft(n, n_fft)
@@ -151,23 +158,42 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     mask_w_fn = mask_w if callable(mask_w) else None
     # ---- step 1
     osn = (S, N) if "use_oracle_" in mask_for_z else None
-    # single-node arrays: no exchange, so the step-1 filter-and-sum and the step-2 SCM share one pass over Y
-    fuse_mid = (K == 1 and mask_for_z == "local" and C <= 8 and mask_w_fn is None)
+    T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
+    # single-node arrays with both masks known: the step-2 statistics are taken over the same Y as the step-1
+    # statistics (tango.py:431-440 with K = 1), so ONE pass accumulates both and ONE pass applies both filters
+    single = (K == 1 and mask_for_z == "local" and mask_w_fn is None and osn is None)
+    same_mask = single and mask_w is mask_z
+    fuse_dual = single and not same_mask and ops.stft_scm_supported(n_fft, C, 2)
+    # otherwise for single-node arrays: the step-1 filter-and-sum and the step-2 SCM share one pass over Y
+    fuse_mid = (single and not same_mask and not fuse_dual and C <= 8)
     # multi-node arrays: z of every node + the step-2 SCMs of every node in one pass over Y
     fuse_multi = (K > 1 and mask_for_z == "local" and mask_w_fn is None and osn is None
                   and ops.tango_mid_supported(C, K))
-    st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn,
-                      apply_filter=not (fuse_mid or fuse_multi))
-    Y, z_y, zn, W1 = st1["Y"], st1["z_y"], st1["zn"], st1["W1"]
-    if mask_w_fn is not None:
-        mask_w = mask_w_fn(Y, z_y, zn)
-    R2 = None
-    if fuse_mid:
-        z_y, zn, Rss2, Rnn2 = ops.filter_sum_scm(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
-        R2 = (Rss2, Rnn2)
-    elif fuse_multi:
-        z_y, zn, Rss2, Rnn2 = ops.tango_mid(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
-        R2 = (Rss2, Rnn2)
+    final_layout = False          # z_y / zn / yf already in `out_layout`
+    R2 = W2 = yf = None
+    if fuse_dual:
+        Y, ws = ops.stft_scm2(y.view(B * K, C, L), mask_z.view(B * K, T, F), mask_w.view(B * K, T, F), n_fft)
+        Y = Y.view(B, K, C, T, F)
+        W12, _ = ops.mwf_solve_workspace2(ws, B * K, C, L, n_fft, mu, filter_type, rank)
+        W1, W2 = W12[0].view(B, K, F, C), W12[1].view(B, K, F, C)
+        z_y, zn, yf = ops.filter_dual(W1, W2, Y, ref=ref_mic, n_fft=n_fft, out_layout=out_layout)
+        final_layout = True
+    else:
+        st1 = tango_step1(y, mask_z, n_fft, mu, filter_type, rank, ref_mic, oracle_sn=osn,
+                          apply_filter=not (fuse_mid or fuse_multi))
+        Y, z_y, zn, W1 = st1["Y"], st1["z_y"], st1["zn"], st1["W1"]
+        if mask_w_fn is not None:
+            mask_w = mask_w_fn(Y, z_y, zn)
+        if same_mask:
+            # K = 1 and mask_w is mask_z (tango.py:388-389): the step-2 statistics ARE the step-1 statistics,
+            # so w_glo = w_loc and yf = z
+            W2 = W1
+        elif fuse_mid:
+            z_y, zn, Rss2, Rnn2 = ops.filter_sum_scm(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
+            R2 = (Rss2, Rnn2)
+        elif fuse_multi:
+            z_y, zn, Rss2, Rnn2 = ops.tango_mid(W1, Y, mask_w, ref=ref_mic, n_fft=n_fft)
+            R2 = (Rss2, Rnn2)
     z_s = z_n = None
     if have_sn and (diagnostics or mask_for_z in ("compressed", "use_oracle_zs")):
         z_s = ops.filter_sum(W1, S, None, conj=True, n_fft=n_fft)
@@ -191,7 +217,13 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     else:   # 'previous' and any other string: unmasked z in both statistics (tango.py:428-429)
         z_rs = z_rn = z_y
     # ---- step 2
-    if R2 is not None:
+    ft = ops._layout(out_layout) == ops.FT
+    conv = ops.transpose_last2 if ft else (lambda a: a)
+    if yf is not None:
+        pass                                                  # fuse_dual: already filtered
+    elif same_mask:
+        yf = conv(z_y) if ft else z_y.clone()
+    elif R2 is not None:
         W2, _ = ops.mwf_solve(R2[0], R2[1], mu, filter_type, rank)
         yf = ops.filter_sum(W2, Y, z_y if K > 1 else None, conj=True, n_fft=n_fft, out_layout=out_layout)
     else:
@@ -200,9 +232,7 @@ def tango_batched(y, s=None, n=None, masks=None, vads=("irm1", "irm1"), mask_for
     if have_sn and diagnostics:
         out["sf"] = ops.filter_sum(W2, S, z_s, conj=True, n_fft=n_fft, out_layout=out_layout)
         out["nf"] = ops.filter_sum(W2, N, z_n, conj=True, n_fft=n_fft, out_layout=out_layout)
-    ft = ops._layout(out_layout) == ops.FT
-    conv = ops.transpose_last2 if ft else (lambda a: a)
-    out["z_y"], out["zn"] = conv(z_y), conv(zn)
+    out["z_y"], out["zn"] = (z_y, zn) if final_layout else (conv(z_y), conv(zn))
     if z_s is not None and diagnostics:
         out["z_s"], out["z_n"] = conv(z_s), conv(z_n)
     out["masks_z"] = conv(mask_z)

@@ -87,14 +87,31 @@ DISCO_API int disco_stft(const float* x, void* Y, int n_sig, int length, int n_f
  *   mask [n_grp] planes of (F, T) float32 in `mask_layout`
  *   Y    [n_grp][C][T][F] complex64                (output, materialised: step 2 re-reads it)
  *   Rss, Rnn [n_grp][F][C][C] complex64            (outputs)
- * C <= 4 in this version (larger arrays: disco_stft + disco_masked_scm).
+ * C <= 8 (n_fft 256 / 512) or C <= 4 (n_fft 1024); disco_stft_scm_supported() tells.  Other shapes:
+ * disco_stft + disco_masked_scm.
  * workspace: disco_stft_scm_workspace() bytes of device scratch.  Rss = Rnn = NULL skips the small
  * reduction launch that materialises the matrices: the per-segment partial sums stay in `workspace`
- * and disco_mwf_solve_workspace() consumes them directly (same summation order, identical result). */
+ * and disco_mwf_solve_workspace() (C <= 4) or disco_scm_from_workspace() consume them (same summation
+ * order, identical result). */
 DISCO_API size_t disco_stft_scm_workspace(int n_grp, int C, int length, int n_fft);
+DISCO_API int disco_stft_scm_supported(int n_fft, int C, int n_mask);
 DISCO_API int disco_stft_scm(const float* x, const float* mask, int mask_layout, void* Y, void* Rss, void* Rnn,
                    int n_grp, int C, int length, int n_fft, void* workspace, size_t workspace_bytes,
                    void* stream);
+
+/* ---- fused STFT + the SCMs under TWO masks (single-node arrays, both masks known up front) --------
+ * For K = 1 the step-2 statistics (reference tango.py:431-440) are taken over the same Y as the step-1
+ * statistics (tango.py:357-364), only under mask_w instead of mask_z.  One pass accumulates both sets, so Y
+ * is written once here and read once by disco_filter_dual() -- never re-read for statistics.
+ *   mask_a, mask_b [n_grp] planes in `mask_layout`; C <= 4, n_fft in {256, 512}.
+ * The four matrix sets stay in `workspace` (disco_stft_scm2_workspace() bytes) as per-segment partial sums:
+ * disco_mwf_solve_workspace2() solves both filter sets from them in one launch; disco_scm_from_workspace()
+ * materialises the matrices of one set (set 0 = mask_a, 1 = mask_b; n_set = 2 here, 1 after disco_stft_scm). */
+DISCO_API size_t disco_stft_scm2_workspace(int n_grp, int C, int length, int n_fft);
+DISCO_API int disco_stft_scm2(const float* x, const float* mask_a, const float* mask_b, int mask_layout, void* Y,
+                    int n_grp, int C, int length, int n_fft, void* workspace, size_t workspace_bytes, void* stream);
+DISCO_API int disco_scm_from_workspace(const void* workspace, int n_set, int set, void* Rss, void* Rnn, int n_grp,
+                             int C, int length, int n_fft, void* stream);
 
 /* ---- oracle time-frequency masks ----------------------------------------------------------------
  * Replaces tf_mask(s, n, type, bin_thr) (reference dnn/utils.py:44-71, sigproc_utils.py:58-86).
@@ -149,6 +166,11 @@ DISCO_API int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T
 DISCO_API int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1, void* Rss, void* Rnn, int n_grp,
                                         int C, int length, int n_fft, int filter_type, int rank, double mu,
                                         void* stream);
+/* Both filter sets of a disco_stft_scm2() workspace in one launch: W, T1 [2][n_grp][F][C]
+ * (set 0 = step-1 filters from mask_a's statistics, set 1 = step-2 filters from mask_b's). */
+DISCO_API int disco_mwf_solve_workspace2(const void* workspace, void* W, void* T1, int n_grp, int C, int length,
+                               int n_fft, int filter_type, int rank, double mu, void* stream);
+
 
 /* ---- filter-and-sum ------------------------------------------------------------------------------
  * Replaces np.inner(conj(w), x[:, f, t]) (conj_w = 1) / np.inner(t1, x[:, f, t]) (conj_w = 0) over
@@ -158,6 +180,14 @@ DISCO_API int disco_mwf_solve_workspace(const void* workspace, void* W, void* T1
 DISCO_API int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
                      int out_layout, int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel,
                      void* stream);
+
+/* ---- both filter-and-sum steps of a single-node array in one pass over Y ---------------------------
+ * Replaces np.inner(conj(w_loc), y) + zn = y[ref] - z (reference tango.py:369-376) AND
+ * np.inner(conj(w_glo), y) (tango.py:445-450 with K = 1: no exchanged signals) for every (f, t):
+ *   W1, W2 [n_grp][F][C]; Y [n_grp][C][T][F]  ->  z, zn (may be NULL), yf [n_grp] planes in `out_layout`.
+ * C <= 4. */
+DISCO_API int disco_filter_dual(const void* W1, const void* W2, const void* Y, void* z, void* zn, void* yf, int ref,
+                      int out_layout, int n_grp, int C, int T, int n_fft, void* stream);
 
 /* ---- inverse STFT --------------------------------------------------------------------------------
  * Replaces lb.core.istft(S, hop_length=n_fft/2, win_length=n_fft, center=True, length=length)

@@ -37,6 +37,12 @@ TANGO_CASES = {
     "tango_k2c2_compressed": (8, [2, 2], 5000, ("irm1", "irm1"), "compressed", ("yf", "z_y")),
     "tango_k2c2_oracle_refs": (9, [2, 2], 5000, ("irm1", "irm1"), "use_oracle_refs", ("yf", "z_y")),
     "tango_k2c2_oracle_zs": (10, [2, 2], 5000, ("irm1", "irm1"), "use_oracle_zs", ("yf", "z_y")),
+    # geometries of BASELINE configs[2] (4 nodes x 4 mics) and configs[4] (8 nodes x 2 mics), short signals
+    "tango_k4c4_local": (12, [4, 4, 4, 4], 8000, ("irm1", "irm1"), "local", ("yf", "z_y")),
+    "tango_k8c2_local": (13, [2] * 8, 6000, ("irm1", "irm1"), "local", ("yf", "z_y")),
+    # single node, two DIFFERENT masks: the two-mask fused route (stft_scm2 + filter_dual) against the reference
+    "tango_k1c4_irm1_irm2": (14, [4], 16000, ("irm1", "irm2"), "local", ("yf", "z_y", "zn")),
+    "tango_k1c3_iam1_irm1": (15, [3], 7000, ("iam1", "irm1"), "local", ("yf", "z_y", "zn")),
 }
 NAMES = ("yf", "sf", "nf", "z_y", "z_s", "z_n", "zn", "masks_z", "mask_w")
 
@@ -63,11 +69,14 @@ def rand_hpd(rng, d, rank=None, dtype=np.complex64):
     return (a @ a.conj().T / r).astype(dtype)
 
 
-def main():
+def main(only=None):
+    """only: iterable of Tango case names to (re)generate; None regenerates every fixture."""
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
 
     for name, (seed, chans, length, vads, mfz, keep) in TANGO_CASES.items():
+        if only is not None and name not in only:
+            continue
         y, s, n = case_inputs(seed, chans, length, vads)
         res = ref_shim.run_offline_tango(y, s, n, vads=vads, mask_for_z=mfz)
         blob = {"input_sha256": np.array(digest(y))}
@@ -84,6 +93,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
         print(name, {k: v.shape for k, v in blob.items() if k.endswith("_0")})
 
+    if only is not None:
+        return
     # ---- intern_filter known answers (complex64 and complex128 inputs, all three types)
     rng = np.random.default_rng(42)
     blob = {}
@@ -310,4 +321,5 @@ def metrics_kat(ref):
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(only=set(sys.argv[1:]) or None)      # python -m oracle.make_golden [case names ...]

@@ -144,6 +144,9 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
     oracle masks with externally supplied ones: (mask_z[K], mask_w[K]) of (F, T) arrays
     (what a DNN would deliver, tango.py:209-215).
     Returns the reference's 9 lists: yf, sf, nf, z_y, z_s, z_n, zn, masks_z, mask_w.
+    Deployment mode (``s is None``: no clean components exist, masks must be given, mask_for_z='local'): the
+    STFTs of s and n and the diagnostic outputs sf, nf, z_s, z_n -- which the reference only computes because
+    its evaluation script has the clean signals -- are skipped (those lists come back as None).
     """
     K = len(y)
     F = n_fft // 2 + 1
@@ -152,8 +155,11 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
         return librosa_np.stft(np.asarray(x), n_fft=n_fft, hop_length=n_hop, center=True)
 
     Y = [np.array([spec(c) for c in y[k]]) for k in range(K)]              # :335
-    S = [np.array([spec(c) for c in s[k]]) for k in range(K)]              # :336
-    N = [np.array([spec(c) for c in n[k]]) for k in range(K)]              # :337
+    deploy = s is None
+    if deploy and (masks is None or mask_for_z != "local"):
+        raise ValueError("deployment mode needs masks and mask_for_z='local'")
+    S = None if deploy else [np.array([spec(c) for c in s[k]]) for k in range(K)]   # :336
+    N = None if deploy else [np.array([spec(c) for c in n[k]]) for k in range(K)]   # :337
     T = Y[0].shape[-1]
 
     def two_outputs():
@@ -180,8 +186,9 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
             Rnn = scm_bin(n_hat[:, f, :], granularity)                      # :364
             w, _ = intern_filter(Rss, Rnn, mu=mu, type=filter_type, rank=rank)   # :367
             z_y[k][f] = apply_bin(w, Y[k][:, f, :], True, granularity)      # :370
-            z_s[k][f] = apply_bin(w, S[k][:, f, :], True, granularity)      # :371
-            z_n[k][f] = apply_bin(w, N[k][:, f, :], True, granularity)      # :372
+            if not deploy:
+                z_s[k][f] = apply_bin(w, S[k][:, f, :], True, granularity)  # :371
+                z_n[k][f] = apply_bin(w, N[k][:, f, :], True, granularity)  # :372
         zn[k] = Y[k][ref_mic] - z_y[k]                                      # :376
 
     # ---- exchange + step-2 masks (tango.py:379-409)
@@ -222,13 +229,17 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
         phi_s_in = concatenate_signals(s_hat_w, z_rs, k, ms)               # :431
         phi_n_in = concatenate_signals(n_hat_w, z_rn, k, mn)               # :432
         in_y = concatenate_signals(Y, z_y, k)                              # :382
-        in_s = concatenate_signals(S, z_s, k)                              # :383
-        in_n = concatenate_signals(N, z_n, k)                              # :384
+        if not deploy:
+            in_s = concatenate_signals(S, z_s, k)                          # :383
+            in_n = concatenate_signals(N, z_n, k)                          # :384
         for f in range(F):
             Rss = scm_bin(phi_s_in[:, f, :], granularity)                   # :433-439
             Rnn = scm_bin(phi_n_in[:, f, :], granularity)                   # :440
             w, _ = intern_filter(Rss, Rnn, mu=mu, type=filter_type, rank=rank)   # :443
             yf[k][f] = apply_bin(w, in_y[:, f, :], True, granularity)       # :446
-            sf[k][f] = apply_bin(w, in_s[:, f, :], True, granularity)       # :447
-            nf[k][f] = apply_bin(w, in_n[:, f, :], True, granularity)       # :448
+            if not deploy:
+                sf[k][f] = apply_bin(w, in_s[:, f, :], True, granularity)   # :447
+                nf[k][f] = apply_bin(w, in_n[:, f, :], True, granularity)   # :448
+    if deploy:
+        sf = nf = z_s = z_n = None
     return yf, sf, nf, z_y, z_s, z_n, zn, masks_z, mask_w

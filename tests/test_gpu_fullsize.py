@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_l2_mag
+from conftest import record_parity, rel_l2_mag
 
 pytestmark = pytest.mark.gpu
 
@@ -73,16 +73,23 @@ def test_cfg3_shape_full_size_properties(dev):
     from disco_b200 import ops
     Y2 = ops.stft(y[:, 2:3].contiguous())
     yf2, _ = tango_step2(Y2, out["z_y"], mw[:, 2:3].contiguous(), node_sel=[2])
-    # (two-kernel route vs the fused middle pass inside tango_batched: same mathematics, different summation order)
-    num = torch.linalg.norm(torch.view_as_real(yf2[:, 0] - out["yf"][:, 2]))
-    # this synthetic source is perfectly coherent across all 16 microphones, so the 7-channel GEVD amplifies
-    # the ~1e-7 differences between the two SCM summation orders by two to three orders of magnitude
-    assert (num / torch.linalg.norm(torch.view_as_real(out["yf"][:, 2]))).item() < 2e-4
-    ref = tango_f64.offline_tango(y[5].cpu().numpy(), masks=(mz[5].cpu().numpy().transpose(0, 2, 1),
-                                                             mw[5].cpu().numpy().transpose(0, 2, 1)))
-    # step 2 solves a 7-channel GEVD on a perfectly coherent source: against EXACT arithmetic the float32
-    # rounding of the spectra is amplified beyond 1e-5 (1.2e-5 measured); the reference's own
-    # single-precision LAPACK path is further away still (see tests/test_gpu_tango.py)
+    # (two-kernel route vs the fused middle pass inside tango_batched: same mathematics, different summation order;
+    # this synthetic source is perfectly coherent across all 16 microphones, so the 7-channel GEVD amplifies the
+    # ~1e-7 differences between two SCM summation orders by two to three orders of magnitude.  Both routes are
+    # therefore judged against float64 with the reference-precision port as the yardstick, utterance 5.)
+    b = 5
+    yb, mzb, mwb = y[b].cpu().numpy(), mz[b].cpu().numpy().transpose(0, 2, 1), mw[b].cpu().numpy().transpose(0, 2, 1)
+    ref = tango_f64.offline_tango(yb, masks=(mzb, mwb))
+    from oracle import tango_np
+    res = tango_np.offline_tango(yb, yb, yb, masks=(mzb, mwb), granularity="bin")
+    port = {"yf": res[0], "z_y": res[3]}
     for k in range(K):
-        assert rel_l2_mag(out["yf"][5, k].cpu().numpy().T, ref["yf"][k]) < 3e-5
-        assert rel_l2_mag(out["z_y"][5, k].cpu().numpy().T, ref["z_y"][k]) < 2e-5
+        for nm in ("yf", "z_y"):
+            got = out[nm][b, k].cpu().numpy().T
+            assert record_parity("cfg3_fullsize_b5", nm, k, err_ref=rel_l2_mag(got, port[nm][k]),
+                                 err_f64=rel_l2_mag(got, ref[nm][k]), ref_f64=rel_l2_mag(port[nm][k], ref[nm][k]),
+                                 note="reference = fp32 port (oracle/tango_np), 10 s, 4 nodes x 4 mics"), (nm, k)
+    got2 = yf2[b, 0].cpu().numpy().T
+    assert record_parity("cfg3_fullsize_b5_two_kernel_route", "yf", 2, err_ref=rel_l2_mag(got2, port["yf"][2]),
+                         err_f64=rel_l2_mag(got2, ref["yf"][2]), ref_f64=rel_l2_mag(port["yf"][2], ref["yf"][2]),
+                         note="tango_step2 (masked_scm + filter_sum) instead of the fused middle pass")

@@ -37,13 +37,18 @@ def test_stft_matches_oracle(dev, n_fft, n_sig, length):
 
 
 @pytest.mark.parametrize("n_fft", [256, 512, 1024])
-@pytest.mark.parametrize("G,C,length", [(1, 2, 64000), (3, 4, 9000), (2, 3, 5003), (5, 1, 4000), (70, 4, 6000)])
+@pytest.mark.parametrize("G,C,length", [(1, 2, 64000), (3, 4, 9000), (2, 3, 5003), (5, 1, 4000), (70, 4, 6000),
+                                        (3, 8, 9000), (70, 6, 6000), (2, 5, 5003), (2, 7, 7001)])
 @pytest.mark.parametrize("layout", ["TF", "FT"])
 def test_stft_scm_matches_oracle(dev, n_fft, G, C, length, layout):
     from disco_b200 import ops
     from oracle import librosa_np, tango_f64
     if layout == "FT" and G > 3:
         pytest.skip("layout variant covered on the small cases")
+    if not ops.stft_scm_supported(n_fft, C, 1):
+        with pytest.raises(NotImplementedError):
+            ops.stft_scm(torch.zeros((G, C, length), device=dev), torch.zeros((G, 1, 1), device=dev), n_fft)
+        pytest.skip("5..8 channels at n_fft=1024 run as stft + masked_scm (register limit, DESIGN 4.1)")
     rng = np.random.default_rng(G * 100 + C)
     x = rng.standard_normal((G, C, length)).astype(np.float32)
     T, F = 1 + length // (n_fft // 2), n_fft // 2 + 1
@@ -63,6 +68,56 @@ def test_stft_scm_matches_oracle(dev, n_fft, G, C, length, layout):
     # deterministic: a second run is bit-identical
     Y2, Rss2, _ = ops.stft_scm(torch.from_numpy(x).to(dev), md, n_fft, mask_layout=layout)
     assert np.array_equal(_np(Rss2), Rss) and np.array_equal(_np(Y2), Y)
+
+
+@pytest.mark.parametrize("n_fft", [256, 512])
+@pytest.mark.parametrize("G,C,length", [(3, 4, 9000), (2, 3, 5003), (5, 1, 4000), (70, 4, 6000), (4, 2, 20000)])
+@pytest.mark.parametrize("layout", ["TF", "FT"])
+def test_stft_scm2_equals_two_single_mask_runs(dev, n_fft, G, C, length, layout):
+    """Two-mask fused STFT+SCM (K = 1 path): both matrix sets and Y are bit-identical to two single-mask runs
+    (same tiles, same summation order), and the two-set solve equals the two single solves."""
+    from disco_b200 import ops
+    if layout == "FT" and G > 3:
+        pytest.skip("layout variant covered on the small cases")
+    rng = np.random.default_rng(G * 31 + C)
+    x = torch.from_numpy(rng.standard_normal((G, C, length)).astype(np.float32)).to(dev)
+    T, F = 1 + length // (n_fft // 2), n_fft // 2 + 1
+    shape = (G, T, F) if layout == "TF" else (G, F, T)
+    ma = torch.from_numpy(rng.uniform(size=shape).astype(np.float32)).to(dev)
+    mb = torch.from_numpy(rng.uniform(size=shape).astype(np.float32)).to(dev)
+    Y2, ws = ops.stft_scm2(x, ma, mb, n_fft, mask_layout=layout)
+    for q, m in enumerate((ma, mb)):
+        Y1, Rss1, Rnn1 = ops.stft_scm(x, m, n_fft, mask_layout=layout)
+        Rss2, Rnn2 = ops.scm_from_workspace(ws, G, C, length, n_fft, n_set=2, set=q)
+        assert torch.equal(Y1, Y2)
+        assert torch.equal(Rss1, Rss2) and torch.equal(Rnn1, Rnn2), q
+    W12, T12 = ops.mwf_solve_workspace2(ws, G, C, length, n_fft)
+    for q, m in enumerate((ma, mb)):
+        _, ws1 = ops.stft_scm(x, m, n_fft, mask_layout=layout, keep_partials=True)
+        W1, T1 = ops.mwf_solve_workspace(ws1, G, C, length, n_fft)
+        assert torch.equal(W12[q], W1) and torch.equal(T12[q], T1), q
+    with pytest.raises(NotImplementedError):
+        ops.stft_scm2(torch.zeros((1, 5, 4000), device=dev), ma[:1], mb[:1], n_fft, mask_layout=layout)
+
+
+@pytest.mark.parametrize("C,ref", [(1, 0), (2, 1), (3, 0), (4, 2)])
+@pytest.mark.parametrize("layout", ["TF", "FT"])
+def test_filter_dual_equals_two_filter_sums(dev, C, ref, layout):
+    """z, zn, yf of the one-pass dual filter == filter_sum(W1, ref) and filter_sum(W2), bit for bit, on odd sizes."""
+    from disco_b200 import ops
+    rng = np.random.default_rng(C)
+    cplx = lambda *s: torch.from_numpy((rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)).to(dev)
+    for (B, T, n_fft) in ((3, 77, 512), (2, 626, 512), (5, 33, 256), (1, 130, 1024)):
+        F = n_fft // 2 + 1
+        Y, W1, W2 = cplx(B, 1, C, T, F), cplx(B, 1, F, C), cplx(B, 1, F, C)
+        z, zn, yf = ops.filter_dual(W1, W2, Y, ref=ref, n_fft=n_fft, out_layout=layout)
+        z1, zn1 = ops.filter_sum(W1, Y, None, conj=True, ref=ref, n_fft=n_fft, out_layout=layout)
+        yf1 = ops.filter_sum(W2, Y, None, conj=True, n_fft=n_fft, out_layout=layout)
+        assert torch.equal(z, z1) and torch.equal(zn, zn1) and torch.equal(yf, yf1), (B, T, n_fft)
+        # against float64
+        want = np.einsum("bkfc,bkctf->bktf", _np(W2).conj().astype(np.complex128), _np(Y).astype(np.complex128))
+        got = _np(yf) if layout == "TF" else _np(yf).transpose(0, 1, 3, 2)
+        assert rel_l2(got, want) < 1e-6
 
 
 @pytest.mark.parametrize("K,C", [(1, 1), (1, 4), (1, 8), (2, 3), (4, 4), (8, 2), (3, 13), (1, 15)])

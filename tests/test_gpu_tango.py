@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_l2_mag
+from conftest import load_golden, record_parity, rel_l2_mag
 from oracle.make_golden import NAMES, TANGO_CASES, case_inputs, digest
 
 pytestmark = pytest.mark.gpu
@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 # the reference's own single-precision LAPACK path can sit further than that from the
 # exact mathematics on ill-conditioned inputs (e.g. 9.9e-5 on tango_k2c4_irm2_iam1); a result then also
 # passes when it is at least as close to the float64 oracle as the reference itself is (+1e-6).
-TOL = 1e-5
+TOL = 1e-5     # == conftest.TOL
 
 
 def f64_truth(name, y, s, n, vads, mfz):
@@ -80,12 +80,14 @@ def test_offline_tango_matches_reference(dev, name):
             else:
                 assert got.dtype == np.complex64
                 err = rel_l2_mag(got, ref)
-                if err >= TOL:
-                    if truth is None:
-                        truth = f64_truth(name, y, s, n, vads, mfz)
-                    assert truth is not None and nm in truth, (key, err)
+                if truth is None:
+                    truth = f64_truth(name, y, s, n, vads, mfz) or {}
+                ours = theirs = None
+                if nm in truth:
                     ours, theirs = rel_l2_mag(got, truth[nm][k]), rel_l2_mag(ref, truth[nm][k])
-                    assert ours <= theirs + 1e-6, (key, err, ours, theirs)
+                ok = record_parity(name, nm, k, err_ref=err, err_f64=ours, ref_f64=theirs,
+                                   note="reference output (tests/golden)")
+                assert ok, (key, err, ours, theirs)
 
 
 def test_tango_batched_matches_f64_and_is_batch_invariant(dev):
@@ -181,13 +183,25 @@ def test_tango_shapes_of_the_stft_sweep_config(dev, n_fft, K, C):
     for b in range(B):
         ref = tango_f64.offline_tango(y[b], masks=(mz[b].transpose(0, 2, 1), mw[b].transpose(0, 2, 1)),
                                       n_fft=n_fft, n_hop=n_fft // 2)
-        # against EXACT arithmetic the budget grows with the channel count (conditioning of the 8-channel
-        # GEVD amplifies the float32 rounding of the spectra; the reference's own single-precision path is
-        # further away still -- parity with the reference at 8 mics is pinned by the tango_k1c8_local fixture)
-        tol = TOL if C <= 4 else 3e-5
+        # against EXACT arithmetic the error grows with the channel count (the conditioning of the 8-channel GEVD
+        # amplifies the float32 rounding of the spectra).  The bar stays the reference: where float64 is further
+        # than TOL, the reference-precision port (oracle/tango_np: complex64 SCMs, single-precision cggev) must be
+        # at least as far from float64 as we are -- recorded per node in the parity table.
+        port = None
         for k in range(K):
-            assert rel_l2_mag(out["yf"][b, k].cpu().numpy(), ref["yf"][k]) < tol
-            assert rel_l2_mag(out["z_y"][b, k].cpu().numpy(), ref["z_y"][k]) < tol
+            for nm in ("yf", "z_y"):
+                got = out[nm][b, k].cpu().numpy()
+                e64 = rel_l2_mag(got, ref[nm][k])
+                eref = pe64 = None
+                if e64 >= TOL:
+                    if port is None:
+                        from oracle import tango_np
+                        res = tango_np.offline_tango(y[b], y[b], y[b], masks=(mz[b].transpose(0, 2, 1), mw[b].transpose(0, 2, 1)),
+                                                     n_fft=n_fft, n_hop=n_fft // 2, granularity="bin")
+                        port = {"yf": res[0], "z_y": res[3]}
+                    eref, pe64 = rel_l2_mag(got, port[nm][k]), rel_l2_mag(port[nm][k], ref[nm][k])
+                assert record_parity("sweep_nfft%d_k%dc%d_b%d" % (n_fft, K, C, b), nm, k, err_ref=eref, err_f64=e64,
+                                     ref_f64=pe64, note="reference = fp32 port (oracle/tango_np)"), (nm, k, e64, pe64)
 
 
 def test_host_pipeline_matches_eager(dev):
