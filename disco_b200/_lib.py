@@ -36,7 +36,7 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_void_p]),
     "disco_tf_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p]),
     "disco_masked_scm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                 c_int, c_int_p, c_int, c_void_p]),
+                                 c_int, c_int_p, c_int, c_int, c_void_p]),
     "disco_filter_sum_scm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p]),
     "disco_tango_mid_supported": (c_int, [c_int, c_int]),
@@ -47,7 +47,7 @@ SIGNATURES = {
     "disco_mwf_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
                                 c_void_p]),
     "disco_filter_sum": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                 c_int, c_int, c_int, c_int_p, c_int, c_void_p]),
+                                 c_int, c_int, c_int, c_int_p, c_int, c_int, c_void_p]),
     "disco_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "disco_scm_recursive": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int_p, c_int, c_void_p]),
@@ -77,7 +77,7 @@ def load():
         fn = getattr(lib, name)     # AttributeError if the ABI symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.disco_abi_version() != 1:
+    if lib.disco_abi_version() != 2:
         raise ImportError("disco_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -231,13 +231,16 @@ int disco_tf_mask(const void* S, const void* N, float* M, size_t n_elem, int kin
 }
 
 static int make_cat(CatArgs* c, const void* Y, const void* Z, int n_utt, int K, int C, int T, int n_fft,
-                    const int* node_sel, int n_sel) {
+                    const int* node_sel, int n_sel, int z_layout = DISCO_Z_UTT_MAJOR) {
     if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (z_layout != DISCO_Z_UTT_MAJOR && z_layout != DISCO_Z_NODE_MAJOR) return fail(DISCO_ERR_INVALID, "bad z_layout");
     if (n_utt <= 0 || K < 1 || C < 1 || T < 1) return fail(DISCO_ERR_INVALID, "bad sizes");
     if (C + K - 1 > 16) return fail(DISCO_ERR_UNSUPPORTED, "C + K - 1 must be <= 16");
     if (!Y || (K > 1 && !Z)) return fail(DISCO_ERR_INVALID, "null pointer");
     c->Y = (const float2*)Y;
     c->Z = (const float2*)Z;
+    c->z_sb = (z_layout == DISCO_Z_NODE_MAJOR) ? 1 : K;
+    c->z_sk = (z_layout == DISCO_Z_NODE_MAJOR) ? n_utt : 1;
     c->C = C;
     c->K = K;
     c->T = T;
@@ -260,10 +263,11 @@ static int make_cat(CatArgs* c, const void* Y, const void* Z, int n_utt, int K, 
 }
 
 int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_layout, void* Rss, void* Rnn,
-                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, void* stream) {
+                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, int z_layout,
+                     void* stream) {
     ScmArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel, z_layout);
     if (rc) return rc;
     if (!Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
     a.mask = mask;
@@ -384,10 +388,10 @@ int disco_mwf_solve(const void* Rss, const void* Rnn, void* W, void* T1, int n_m
 
 int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
                      int out_layout, int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel,
-                     void* stream) {
+                     int z_layout, void* stream) {
     FilterArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
+    int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel, z_layout);
     if (rc) return rc;
     if (!W || !out) return fail(DISCO_ERR_INVALID, "null pointer");
     if (ref < 0 || ref >= C + K - 1) return fail(DISCO_ERR_INVALID, "ref channel out of range");

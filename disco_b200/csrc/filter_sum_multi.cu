@@ -126,7 +126,7 @@ static cudaError_t launch_fsm(const FilterArgs& a, cudaStream_t st) {
 // All K nodes, frame-major output, an instantiated (C, K): otherwise cudaErrorNotSupported and the caller
 // keeps the per-node kernel.
 cudaError_t launch_filter_sum_multi(const FilterArgs& a, cudaStream_t st) {
-    if (a.in.K < 2 || a.in.n_sel != a.in.K || a.out_ft || !a.in.Z) return cudaErrorNotSupported;
+    if (a.in.K < 2 || a.in.n_sel != a.in.K || a.out_ft || !a.in.Z || a.in.z_sk != 1) return cudaErrorNotSupported;
 #define FSM_CASE(c, k) \
     if (a.in.C == c && a.in.K == k) return launch_fsm<c, k>(a, st);
     FSM_CASE(1, 2) FSM_CASE(2, 2) FSM_CASE(3, 2) FSM_CASE(4, 2)

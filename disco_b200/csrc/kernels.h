@@ -37,7 +37,9 @@ int stft_cta_of_tile_host(long long i, long long total, int nb);
 // channel count on the subset `sel` of nodes that have C microphones: group g = (b, sel[g % n_sel]).
 struct CatArgs {
     const float2* Y;   // [n_grp][C][T][F]
-    const float2* Z;   // [n_utt][K][T][F]   (may be null when K == 1)
+    const float2* Z;   // [n_utt][K][T][F] (z_sb = K, z_sk = 1) or node-major [K][n_utt][T][F] (z_sb = 1, z_sk = n_utt);
+                       // may be null when K == 1
+    long long z_sb, z_sk;   // plane (T x F) strides of Z along the utterance and the node axis
     int C, K, T, F;
     int n_grp;         // = n_utt * n_sel
     int n_sel;         // nodes covered by this launch (K when all nodes have C microphones)

@@ -21,7 +21,7 @@ DISCO_DEV const float2* online_channel(const CatArgs& in, int grp, int d) {
     const int b = grp / in.n_sel, k = in.sel[grp % in.n_sel];
     int j = d - in.C;
     if (j >= k) ++j;  // skip own compressed signal (tango.py:153-155)
-    return in.Z + ((size_t)b * in.K + j) * in.T * in.F;
+    return in.Z + ((size_t)b * in.z_sb + (size_t)j * in.z_sk) * in.T * in.F;
 }
 
 constexpr int kOnlineBY = 4;   // blocks of frames per CTA (threadIdx.y)

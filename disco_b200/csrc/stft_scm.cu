@@ -90,13 +90,15 @@ __host__ __device__ __forceinline__ int cta_of_tile(long long i, long long total
     return b;
 }
 
-template <int R>
-DISCO_DEV void set_maxnreg_inc() {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R));
-}
-template <int R>
-DISCO_DEV void set_maxnreg_dec() {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(R));
+// Warpgroup register reallocation: grow (inc) or shrink (dec) relative to the launch allocation; the PTX
+// rules make the wrong direction undefined behaviour (an illegal-instruction fault on sm_100a).
+template <int R, int LAUNCH>
+DISCO_DEV void set_maxnreg() {
+    if constexpr (R > LAUNCH) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R));
+    } else if constexpr (R < LAUNCH) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(R));
+    }
 }
 
 // Accumulators of one bin: per mask, C diagonal pairs (s-weighted, n-weighted) and C(C-1)/2
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
     };
 
     if (warp < G::LEAD_WARPS) {
-        if (G::REALLOC) set_maxnreg_dec<G::REG_LEAD>();
+        if (G::REALLOC) set_maxnreg<G::REG_LEAD, G::REG_LAUNCH>();
         if (warp != 0) return;
         // =========================================================== LOADER (+ Nyquist bin)
         auto load_tile = [&](int it) {
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
             __syncwarp();   // nyq[] is rewritten by the next tile
         }
     } else if (warp < G::LEAD_WARPS + G::FFT_WARPS) {
-        if (G::REALLOC) set_maxnreg_inc<G::REG_FFT>();
+        if (G::REALLOC) set_maxnreg<G::REG_FFT, G::REG_LAUNCH>();
         // =========================================================== FFT warps
         const int w = warp - G::LEAD_WARPS;
         constexpr bool WINREG = (RA <= 16);
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
             if (lane == 0) mbar_arrive(&spec_full[s]);
         }
     } else {
-        if (G::REALLOC) set_maxnreg_inc<G::REG_SCM>();
+        if (G::REALLOC) set_maxnreg<G::REG_SCM, G::REG_LAUNCH>();
         // =========================================================== SCM warps: thread <-> bin f
         const int f = (warp - G::LEAD_WARPS - G::FFT_WARPS) * 32 + lane;   // 0 .. N/2 - 1
         const int fn = (N - f) & (N - 1);

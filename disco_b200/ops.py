@@ -248,17 +248,27 @@ def _sel(node_sel, K):
     return arr, len(node_sel), len(node_sel)
 
 
+def _z_dims(Z, B, T, F, z_layout):
+    """K and the layout flag of the exchanged signals: 'BK' = [B, K, T, F], 'KB' = node-major [K, B, T, F]
+    (what an all-gather over node-owning ranks delivers, disco_b200/dist.py)."""
+    if z_layout not in ("BK", "KB"):
+        raise ValueError("z_layout must be 'BK' or 'KB'")
+    _need(Z, torch.complex64, "Z")
+    K = Z.shape[1] if z_layout == "BK" else Z.shape[0]
+    want = (B, K, T, F) if z_layout == "BK" else (K, B, T, F)
+    if tuple(Z.shape) != want:
+        raise ValueError("Z shape %s, expected %s" % (tuple(Z.shape), want))
+    return K, (0 if z_layout == "BK" else 1)
+
+
 @_on_device
-def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
-    """Y [B, Ksel, C, T, F], Z [B, K, T, F] or None (K = 1), mask [B, Ksel, T, F] / [B, Ksel, F, T] or None
+def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None, z_layout="BK"):
+    """Y [B, Ksel, C, T, F], Z [B, K, T, F] (or [K, B, T, F] with z_layout='KB') or None (K = 1),
+    mask [B, Ksel, T, F] / [B, Ksel, F, T] or None
     -> Rss, Rnn [B, Ksel, F, D, D], D = C + K - 1 (own mics, then z of the other nodes)."""
     _need(Y, torch.complex64, "Y")
     B, Ks, C, T, F = Y.shape
-    K = 1 if Z is None else Z.shape[1]
-    if Z is not None:
-        _need(Z, torch.complex64, "Z")
-        if tuple(Z.shape) != (B, K, T, F):
-            raise ValueError("Z must be [B, K, T, F]")
+    K, zl = (1, 0) if Z is None else _z_dims(Z, B, T, F, z_layout)
     n_utt = B
     if Z is None:            # no exchange: every (b, k) is an independent single-node problem
         n_utt, sel, n_sel = B * Ks, None, 1
@@ -276,7 +286,7 @@ def masked_scm(Y, mask, Z=None, n_fft=512, mask_layout="TF", node_sel=None):
     Rss = torch.empty((B, Ks, F, D, D), dtype=torch.complex64, device=Y.device)
     Rnn = torch.empty_like(Rss)
     _lib.check(_lib.load().disco_masked_scm(_ptr(Y), _ptr(Z), _ptr(mask), lay, _ptr(Rss), _ptr(Rnn), n_utt, K, C, T,
-                                            n_fft, sel, n_sel, _stream()))
+                                            n_fft, sel, n_sel, zl, _stream()))
     return Rss, Rnn
 
 
@@ -349,15 +359,14 @@ def mwf_solve(Rss, Rnn, mu=1.0, type="gevd", rank=1):
 
 
 @_on_device
-def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", node_sel=None):
+def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", node_sel=None, z_layout="BK"):
     """out = w^H x (conj=True) or w^T x over the concatenated channels [Y ; z of other nodes].
-    W [B, Ksel, F, D]; returns out (and resid = x[ref] - out when ref is given), [B, Ksel, T, F] or [.., F, T]."""
+    W [B, Ksel, F, D]; Z [B, K, T, F] (or [K, B, T, F] with z_layout='KB');
+    returns out (and resid = x[ref] - out when ref is given), [B, Ksel, T, F] or [.., F, T]."""
     _need(W, torch.complex64, "W")
     _need(Y, torch.complex64, "Y")
     B, Ks, C, T, F = Y.shape
-    K = 1 if Z is None else Z.shape[1]
-    if Z is not None:
-        _need(Z, torch.complex64, "Z")
+    K, zl = (1, 0) if Z is None else _z_dims(Z, B, T, F, z_layout)
     n_utt = B
     if Z is None:
         n_utt, sel, n_sel = B * Ks, None, 1
@@ -374,7 +383,7 @@ def filter_sum(W, Y, Z=None, conj=True, ref=None, n_fft=512, out_layout="TF", no
     resid = torch.empty_like(out) if ref is not None else None
     _lib.check(_lib.load().disco_filter_sum(_ptr(W), 1 if conj else 0, _ptr(Y), _ptr(Z), _ptr(out), _ptr(resid),
                                             0 if ref is None else int(ref), lay, n_utt, K, C, T, n_fft, sel, n_sel,
-                                            _stream()))
+                                            zl, _stream()))
     return (out, resid) if ref is not None else out
 
 

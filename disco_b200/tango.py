@@ -94,18 +94,20 @@ def tango_step1(y, mask_z, n_fft=512, mu=1.0, filter_type="gevd", rank=1, ref_mi
 
 
 def tango_step2(Y, Z, mask_w, n_fft=512, mu=1.0, filter_type="gevd", rank=1, out_layout="TF", node_sel=None,
-                z_rs=None, z_rn=None):
+                z_rs=None, z_rn=None, z_layout="BK"):
     """Y [B, Ksel, C, T, F], Z [B, K, T, F] (all nodes' compressed signals), mask_w [B, Ksel, T, F].
     mask_for_z='local' when z_rs / z_rn are None; otherwise they are the [B, K, T, F] signals the
     other nodes contribute to the speech / noise statistics (own channels are still masked by mask_w).
+    z_layout='KB': Z (and z_rs / z_rn) are node-major [K, B, T, F], as an all-gather over node-owning ranks
+    delivers them (disco_b200/dist.py).
     Returns yf [B, Ksel, ...], W2 [B, Ksel, F, D]."""
     if z_rs is None:
-        Rss, Rnn = ops.masked_scm(Y, mask_w, Z, n_fft, node_sel=node_sel)
+        Rss, Rnn = ops.masked_scm(Y, mask_w, Z, n_fft, node_sel=node_sel, z_layout=z_layout)
     else:
-        Rss, _ = ops.masked_scm(_bcast_mask(Y, mask_w, False), None, z_rs, n_fft, node_sel=node_sel)
-        Rnn, _ = ops.masked_scm(_bcast_mask(Y, mask_w, True), None, z_rn, n_fft, node_sel=node_sel)
+        Rss, _ = ops.masked_scm(_bcast_mask(Y, mask_w, False), None, z_rs, n_fft, node_sel=node_sel, z_layout=z_layout)
+        Rnn, _ = ops.masked_scm(_bcast_mask(Y, mask_w, True), None, z_rn, n_fft, node_sel=node_sel, z_layout=z_layout)
     W2, _ = ops.mwf_solve(Rss, Rnn, mu, filter_type, rank)
-    yf = ops.filter_sum(W2, Y, Z, conj=True, n_fft=n_fft, out_layout=out_layout, node_sel=node_sel)
+    yf = ops.filter_sum(W2, Y, Z, conj=True, n_fft=n_fft, out_layout=out_layout, node_sel=node_sel, z_layout=z_layout)
     return yf, W2
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DISCO_ABI_VERSION 1
+#define DISCO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DISCO_API __attribute__((visibility("default")))
@@ -48,6 +48,10 @@ extern "C" {
 /* layouts of (F, T) planes */
 #define DISCO_LAYOUT_TF 0 /* frame-major: [T][F], bins contiguous (native)                      */
 #define DISCO_LAYOUT_FT 1 /* reference NumPy layout: [F][T], frames contiguous                   */
+
+/* layout of the exchanged compressed signals Z (all nodes of all utterances) */
+#define DISCO_Z_UTT_MAJOR 0  /* [n_utt][K][T][F]: what one GPU holding every node produces            */
+#define DISCO_Z_NODE_MAJOR 1 /* [K][n_utt][T][F]: what an all-gather over node-owning ranks delivers   */
 
 /* tf_mask kinds (reference dnn/utils.py:44-71 `type` = 'irmX' | 'ibmX' | 'iamX') */
 #define DISCO_MASK_IRM 0
@@ -128,9 +132,12 @@ DISCO_API int disco_tf_mask(const void* S, const void* N, float* M, size_t n_ele
  * launch once per channel count with node_sel = the ascending HOST array of the n_sel node
  * indices that have C microphones (Y, mask, outputs then hold n_utt * n_sel groups);
  * node_sel == NULL means all K nodes.
- *   Y [n_utt*K][C][T][F], Z [n_utt][K][T][F] complex64; mask [n_utt*K] planes; Rss/Rnn [n_utt*K][F][D][D] */
+ *   Y [n_utt*K][C][T][F], Z [n_utt][K][T][F] complex64; mask [n_utt*K] planes; Rss/Rnn [n_utt*K][F][D][D]
+ * z_layout = DISCO_Z_NODE_MAJOR reads Z as [K][n_utt][T][F] -- the buffer an NCCL all-gather over node-owning
+ * ranks fills (the reference's exchange, tango.py:379-386) -- so the gathered signals are never transposed. */
 DISCO_API int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_layout, void* Rss, void* Rnn,
-                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, void* stream);
+                     int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel, int z_layout,
+                     void* stream);
 
 /* ---- fused step-1 filter-and-sum + step-2 masked SCM for single-node groups (K = 1) ----------------
  * One pass over Y instead of two: z = w1^H y and zn = y[ref] - z (reference tango.py:369-376) are
@@ -179,7 +186,7 @@ DISCO_API int disco_mwf_solve_workspace2(const void* workspace, void* W, void* T
  *   W [n_utt*K][F][D]; out, resid [n_utt*K] planes in `out_layout` (resid may be NULL) */
 DISCO_API int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, void* out, void* resid, int ref,
                      int out_layout, int n_utt, int K, int C, int T, int n_fft, const int* node_sel, int n_sel,
-                     void* stream);
+                     int z_layout, void* stream);
 
 /* ---- both filter-and-sum steps of a single-node array in one pass over Y ---------------------------
  * Replaces np.inner(conj(w_loc), y) + zn = y[ref] - z (reference tango.py:369-376) AND

@@ -25,7 +25,7 @@ def test_header_symbols_exported(lib):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.disco_abi_version() == 1
+    assert lib.disco_abi_version() == 2
 
 
 def test_n_frames_matches_reference_formula(lib):
@@ -45,6 +45,14 @@ def test_argument_validation_without_gpu(lib):
     assert lib.disco_mwf_solve(None, None, None, None, 1, 17, 0, 1, 1.0, None) == -2
     assert lib.disco_tf_mask(None, None, None, 10, 5, 1, 0.0, None) == -1
     assert lib.disco_stft_scm_workspace(64, 4, 160000, 512) > 0
+    assert lib.disco_stft_scm2_workspace(64, 4, 160000, 512) == 2 * lib.disco_stft_scm_workspace(64, 4, 160000, 512)
+    # which (n_fft, channels, masks) the fused STFT+SCM kernel covers: up to 8 mics, two masks up to 4 mics
+    sup = lib.disco_stft_scm_supported
+    assert sup(512, 8, 1) and sup(256, 5, 1) and sup(512, 4, 2) and sup(1024, 4, 1)
+    assert not sup(1024, 8, 1) and not sup(512, 8, 2) and not sup(512, 9, 1) and not sup(1024, 4, 2)
+    assert lib.disco_filter_dual(None, None, None, None, None, None, 0, 0, 1, 4, 10, 512, None) == -1
+    assert lib.disco_masked_scm(None, None, None, 0, None, None, 1, 2, 2, 10, 512, None, 0, 7, None) == -1   # bad z_layout
+    assert b"z_layout" in lib.disco_last_error()
     with pytest.raises(_lib.DiscoError):
         _lib.check(lib.disco_init(300))
 

@@ -46,13 +46,15 @@ def _oracle_step1(y, mask_z, **kw):
     return {"Y": torch.from_numpy(np.array(Ys))[:, None], "z_y": torch.from_numpy(np.array(zs))[:, None]}
 
 
-def _oracle_step2(Y, Z, mask_w, node, **kw):
+def _oracle_step2(Y, Z, mask_w, nodes, **kw):
+    """Z node-major [K, B, T, F] (what the all-gather delivers); one local node per rank here."""
     from oracle import tango_f64
-    B, K = Z.shape[:2]
+    K, B = Z.shape[:2]
+    node = list(nodes)[0]
     out = []
     for b in range(B):
         others = [j for j in range(K) if j != node]
-        X = np.concatenate([Y[b, 0].numpy().transpose(0, 2, 1), Z[b, others].numpy().transpose(0, 2, 1)], axis=0)
+        X = np.concatenate([Y[b, 0].numpy().transpose(0, 2, 1), Z[others, b].numpy().transpose(0, 2, 1)], axis=0)
         Rss, Rnn = tango_f64.masked_scm(X, mask_w[b, 0].numpy().T)
         out.append(tango_f64.filter_sum(tango_f64.solve(Rss, Rnn), X).T)
     return torch.from_numpy(np.array(out))[:, None]
@@ -65,27 +67,44 @@ def _worker(rank, world, port, L, q):
     try:
         from disco_b200.synth import make_batch
         from oracle import tango_f64
-        B, C = 2, 2
+        B, C = 3, 2
         y, s, n = make_batch(B, world, C, L, seed0=11)
         T, F = 1 + L // 256, 257
         masks = np.stack([[tango_f64.irm(tango_f64.stft64(s[b, k, 0]), tango_f64.stft64(n[b, k, 0])).T
                            for k in range(world)] for b in range(B)])                     # [B, K, T, F]
         # order check of the gather itself
         tag = torch.full((B, 3), float(rank))
-        G = all_gather_nodes(tag)
-        assert G.shape == (B, world, 3) and all(float(G[0, k, 0]) == k for k in range(world))
-        zc = torch.full((B, 2, 2), complex(rank, -rank), dtype=torch.complex128)
-        Gc = all_gather_nodes(zc)
-        assert Gc.dtype == torch.complex128 and Gc[1, 1, 0, 0] == complex(1, -1)
-        res = tango_node_sharded(torch.from_numpy(y[:, rank:rank + 1]), torch.from_numpy(masks[:, rank:rank + 1]),
-                                 step1=_oracle_step1, step2=_oracle_step2)
+        G = all_gather_nodes(tag)                       # one node per rank, [B, ...] form -> node-major [K, B, ...]
+        assert G.shape == (world, B, 3) and all(float(G[k, 0, 0]) == k for k in range(world))
+        zc = torch.full((B, 2, 2, 2), complex(rank, -rank), dtype=torch.complex128)     # [B, Kl = 2, T, F]
+        zc[:, 1] += 10
+        Gc = all_gather_nodes(zc)                       # two nodes per rank: node k = rank k // 2, local k % 2
+        assert Gc.dtype == torch.complex128 and Gc.shape == (2 * world, B, 2, 2)
+        assert Gc[2, 1, 0, 0] == complex(1, -1) and Gc[3, 0, 1, 1] == complex(11, -1) and Gc[1, 2, 0, 0] == complex(10, 0)
         ok = True
-        for b in range(B):
-            ref = tango_f64.offline_tango(y[b], s[b], n[b])
-            err = np.linalg.norm(res["yf"][b, 0].numpy().T - ref["yf"][rank]) / np.linalg.norm(ref["yf"][rank])
-            ok = ok and err < 1e-9
-            errz = np.abs(res["Z"][b].numpy().transpose(0, 2, 1) - ref["z_y"]).max()
-            ok = ok and errz < 1e-9
+        calls = {"s1": [], "s2": []}
+
+        def s1(y_, m_, ref_mic=0):                      # explicit signatures, like the GPU callables
+            calls["s1"].append({"ref_mic": ref_mic})
+            return _oracle_step1(y_, m_)
+
+        def s2(Y_, Z_, m_, nodes, out_layout="TF"):
+            calls["s2"].append({"out_layout": out_layout})
+            return _oracle_step2(Y_, Z_, m_, nodes)
+        for chunks in (1, 2):
+            res = tango_node_sharded(torch.from_numpy(y[:, rank:rank + 1]), torch.from_numpy(masks[:, rank:rank + 1]),
+                                     step1=s1, step2=s2, chunks=chunks, ref_mic=0, out_layout="TF")
+            assert len(res["Z"]) == chunks and res["yf"].shape[0] == B
+            Zall = torch.cat(res["Z"], dim=1)            # [K, B, T, F]
+            for b in range(B):
+                ref = tango_f64.offline_tango(y[b], s[b], n[b])
+                err = np.linalg.norm(res["yf"][b, 0].numpy().T - ref["yf"][rank]) / np.linalg.norm(ref["yf"][rank])
+                ok = ok and err < 1e-9
+                errz = np.abs(Zall[:, b].numpy().transpose(0, 2, 1) - ref["z_y"]).max()
+                ok = ok and errz < 1e-9
+        # step-specific keywords reach only the step that takes them (ref_mic: step 1, out_layout: step 2);
+        # passing both used to raise a TypeError in the other step
+        ok = ok and len(calls["s1"]) == 3 and len(calls["s2"]) == 3
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

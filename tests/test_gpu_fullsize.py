@@ -18,12 +18,18 @@ def dev():
 
 
 def _inputs(dev, B, K, C, L, seed):
+    """Coherent source + white noise per microphone; masks = irm1 / irm2 of the reference channel's clean
+    components (informative masks: with masks independent of the signal R_ss ~ c R_nn, a degenerate GEVD whose
+    principal eigenvector amplifies last-bit differences between summation orders a thousandfold)."""
+    from disco_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(seed)
-    T, F = 1 + L // 256, 257
     src = 0.1 * torch.randn((B, 1, 1, L), generator=g)
-    y = (src * (0.5 + torch.rand((B, K, C, 1), generator=g)) + 0.05 * torch.randn((B, K, C, L), generator=g)).to(dev)
-    mz = torch.rand((B, K, T, F), generator=g).clamp_(0.02, 0.98).to(dev)
-    mw = torch.rand((B, K, T, F), generator=g).clamp_(0.02, 0.98).to(dev)
+    s = (src * (0.5 + torch.rand((B, K, C, 1), generator=g))).to(dev)
+    n = (0.05 * torch.randn((B, K, C, L), generator=g)).to(dev)
+    y = s + n
+    S, N = ops.stft(s[:, :, 0].contiguous()), ops.stft(n[:, :, 0].contiguous())
+    mz = ops.tf_mask(S, N, "irm1").clamp_(0.02, 0.98)
+    mw = ops.tf_mask(S, N, "irm2").clamp_(0.02, 0.98)
     return y, mz, mw
 
 
@@ -41,10 +47,18 @@ def test_cfg2_full_size_properties(dev):
     # (1) homogeneity: the MWF weights are invariant to a common gain, so yf(a y) = a yf(y)
     out2 = tango_batched(2.0 * y, masks=(mz, mw), **kw)     # power of two: exact in floating point
     assert torch.equal(out2["yf"], 2.0 * out["yf"])
-    # (2) utterances do not interact: permuting the batch permutes the outputs bit for bit
+    # (2) utterances do not interact: permuting the batch permutes the outputs.  Not bit for bit: the persistent
+    # fused kernel cuts the frame axis of an utterance where its CTA ranges end, which depends on the position in
+    # the batch, so the partial sums of the SCMs are added in a different order (a few 1e-7 on the matrices)
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).to(dev)
     outp = tango_batched(y[perm].contiguous(), masks=(mz[perm].contiguous(), mw[perm].contiguous()), **kw)
-    assert torch.equal(outp["yf"], out["yf"][perm])
+    for nm in ("yf", "z_y"):
+        a, b = outp[nm].abs(), out[nm][perm].abs()
+        err = torch.linalg.norm((a - b).flatten(1), dim=1) / torch.linalg.norm(b.flatten(1), dim=1)
+        assert err.max().item() < 1e-5, (nm, err.max().item())
+    # ... and a batch processed twice in the same order is reproduced bit for bit (no atomics anywhere)
+    again = tango_batched(y, masks=(mz, mw), **kw)
+    assert torch.equal(again["yf"], out["yf"]) and torch.equal(again["z_y"], out["z_y"])
     # (3) zn + z = reference microphone spectrum; iSTFT(STFT(y)) = y
     Y = ops.stft(y)
     assert torch.allclose(torch.view_as_real(out["zn"] + out["z_y"]), torch.view_as_real(Y[:, :, 0]), atol=2e-5)
