@@ -9,12 +9,34 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// tuning knobs (scripts/build_variants.py builds alternatives for A/B runs; the defaults are the measured best)
+#ifndef DISCO_FD_UF
+#define DISCO_FD_UF 2          // frames per thread and register buffer (frame-major output)
+#endif
+#ifndef DISCO_FD_MINB
+#define DISCO_FD_MINB 2        // resident CTAs per SM the register allocation aims for
+#endif
+#ifndef DISCO_FD_WANT
+#define DISCO_FD_WANT 4        // CTAs per SM the time split aims for (equal-sized CTAs: more waves, shorter tail)
+#endif
+#ifndef DISCO_FD_STCS
+#define DISCO_FD_STCS 0        // 1: streaming (evict-first) stores for the three outputs
+#endif
+
 namespace disco {
 
+DISCO_DEV void fd_store(float2* p, float2 v) {
+#if DISCO_FD_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 template <int C, bool OUT_FT>
-__global__ void __launch_bounds__(256, 2) filter_dual_kernel(DualFilterArgs a, int frames_per_slab) {
+__global__ void __launch_bounds__(256, DISCO_FD_MINB) filter_dual_kernel(DualFilterArgs a, int frames_per_slab) {
     constexpr int TS = 8;                         // warps per block = time ways
-    constexpr int UF = OUT_FT ? 4 : 2;            // frames per thread and buffer
+    constexpr int UF = OUT_FT ? 4 : DISCO_FD_UF;  // frames per thread and buffer
     __shared__ float2 tile[OUT_FT ? 3 : 1][OUT_FT ? 32 : 1][33];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int grp = blockIdx.y;
@@ -64,9 +86,9 @@ __global__ void __launch_bounds__(256, 2) filter_dual_kernel(DualFilterArgs a, i
             const float2 zn = csub(r, z);
             if (!OUT_FT) {
                 if (tt < t_end) {
-                    a.z[go + (size_t)tt * F + f] = z;
-                    if (a.zn) a.zn[go + (size_t)tt * F + f] = zn;
-                    a.yf[go + (size_t)tt * F + f] = yf;
+                    fd_store(a.z + go + (size_t)tt * F + f, z);
+                    if (a.zn) fd_store(a.zn + go + (size_t)tt * F + f, zn);
+                    fd_store(a.yf + go + (size_t)tt * F + f, yf);
                 }
             } else {
                 const int tl = wrp * UF + u;
@@ -109,7 +131,7 @@ static cudaError_t launch_c(const DualFilterArgs& a, int sm, cudaStream_t st) {
     const int fblocks = (a.F + 31) / 32;
     // enough CTAs to fill the machine: split time into slabs (multiples of 32 frames) when groups are few
     int slabs = 1;
-    const int want = sm * 4;
+    const int want = sm * DISCO_FD_WANT;
     while (fblocks * a.n_grp * slabs < want && (a.T + slabs - 1) / slabs > 64) slabs *= 2;
     const int fps = ((a.T + slabs - 1) / slabs + 31) / 32 * 32;
     slabs = (a.T + fps - 1) / fps;

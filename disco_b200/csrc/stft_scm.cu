@@ -37,6 +37,14 @@
 #include "fft_reg.cuh"
 #include "kernels.h"
 
+// tuning knobs (scripts/build_variants.py builds alternatives for A/B runs; the defaults are the measured best)
+#ifndef DISCO_SS_PF
+#define DISCO_SS_PF 0          // tiles ahead of the TMA load that the loader prefetches into L2 (0 = off)
+#endif
+#ifndef DISCO_SS_FW
+#define DISCO_SS_FW 8          // FFT warps for up to 4 microphones (8 jobs per tile: 8 or 4)
+#endif
+
 namespace disco {
 
 template <int N, int C>
@@ -53,7 +61,7 @@ struct StftCfg {
     // Roles on warpgroup boundaries + setmaxnreg: the SCM warps of wide arrays (128 accumulators) and of
     // two-mask runs (64) need more registers than an even split of the register file gives them.
     static constexpr bool REALLOC = (N == 512) || (WIDE && N == 256);
-    static constexpr int FFT_WARPS = (WIDE && N == 512) ? 4 : 8;
+    static constexpr int FFT_WARPS = (WIDE && N == 512) ? 4 : (WIDE ? 8 : DISCO_SS_FW);
     static constexpr int JPW = JOBS / FFT_WARPS;   // jobs per FFT warp and tile
     static constexpr int ROWP = 1056 / NB;         // spectrum row pitch (complex): a job = 32 x 33 scratch
     static constexpr int SCM_WARPS = N / 64;       // bins 0 .. N/2-1, one per thread
@@ -283,9 +291,24 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
 #pragma unroll
                 for (int u = 0; u < NSLOT; ++u) as[q][u] = an[q][u] = 0.f;
         };
+        // L2 prefetch of the in-range samples of tile `it` (DISCO_SS_PF tiles ahead of its TMA load)
+        auto prefetch_tile = [&](int it) {
+            if (!p.use_tma || it >= n_it) return;
+            int grp, t0;
+            tile_of(it, grp, t0);
+            const int nfr = min(TT, T - t0), c_valid = min(C, p.n_sig - grp * C);
+            const int s0 = t0 * H - H, cnt = (nfr + 1) * H;
+            const int k_lo = max(0, -s0), k_hi = min(cnt, L - s0);
+            if (k_hi > k_lo && lane < c_valid)
+                tma_prefetch_l2(p.x + ((size_t)grp * C + lane) * L + s0 + k_lo, (uint32_t)((k_hi - k_lo) * sizeof(float)));
+        };
         nyq_reset();
+        if (DISCO_SS_PF > 0) {
+            for (int i = 1; i <= DISCO_SS_PF; ++i) prefetch_tile(i);
+        }
         load_tile(0);
         for (int it = 0; it < n_it; ++it) {
+            if (DISCO_SS_PF > 0) prefetch_tile(it + 1 + DISCO_SS_PF);
             if (it + 1 < n_it) load_tile(it + 1);
             int grp, t0;
             tile_of(it, grp, t0);

@@ -104,13 +104,13 @@ def stft_scm(x, mask, n_fft=512, mask_layout="TF", keep_partials=False):
         raise ValueError("x must be [groups, channels, samples]")
     G, C, L = x.shape
     T, F = n_frames(L, n_fft), n_fft // 2 + 1
+    lib = _lib.load()
+    if not lib.disco_stft_scm_supported(n_fft, C, 1):
+        raise NotImplementedError("fused STFT+SCM: %d channels at n_fft=%d (use stft + masked_scm)" % (C, n_fft))
     lay = _layout(mask_layout)
     want = (G, T, F) if lay == TF else (G, F, T)
     if tuple(mask.shape) != want:
         raise ValueError("mask shape %s, expected %s" % (tuple(mask.shape), want))
-    lib = _lib.load()
-    if not lib.disco_stft_scm_supported(n_fft, C, 1):
-        raise NotImplementedError("fused STFT+SCM: %d channels at n_fft=%d (use stft + masked_scm)" % (C, n_fft))
     Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
     ws_bytes = lib.disco_stft_scm_workspace(G, C, L, n_fft)
     ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
@@ -162,13 +162,13 @@ def stft_scm2(x, mask_a, mask_b, n_fft=512, mask_layout="TF"):
         raise ValueError("x must be [groups, channels, samples]")
     G, C, L = x.shape
     T, F = n_frames(L, n_fft), n_fft // 2 + 1
+    lib = _lib.load()
+    if not lib.disco_stft_scm_supported(n_fft, C, 2):
+        raise NotImplementedError("two-mask fused STFT+SCM: %d channels at n_fft=%d" % (C, n_fft))
     lay = _layout(mask_layout)
     want = (G, T, F) if lay == TF else (G, F, T)
     if tuple(mask_a.shape) != want or tuple(mask_b.shape) != want:
         raise ValueError("mask shapes %s / %s, expected %s" % (tuple(mask_a.shape), tuple(mask_b.shape), want))
-    lib = _lib.load()
-    if not lib.disco_stft_scm_supported(n_fft, C, 2):
-        raise NotImplementedError("two-mask fused STFT+SCM: %d channels at n_fft=%d" % (C, n_fft))
     Y = torch.empty((G, C, T, F), dtype=torch.complex64, device=x.device)
     ws_bytes = lib.disco_stft_scm2_workspace(G, C, L, n_fft)
     ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=x.device)
