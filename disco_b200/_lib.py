@@ -59,6 +59,7 @@ SIGNATURES = {
     "disco_transpose_c64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "disco_transpose_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "disco_apply_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "disco_apply_mask_channels": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_size_t, c_int, c_void_p]),
 }
 
 _lib = None

@@ -2,6 +2,7 @@
 import numpy as np
 
 from ..tango import offline_tango  # noqa: F401  (reference signature, tango.py:252)
+from ._util import DEVICE
 from .sigproc_utils import tf_mask, vad_oracle_batch
 
 N_FFT = 512          # tango.py:28
@@ -47,11 +48,18 @@ def reshape_mask(mask, output_frame="last"):
 
 
 def get_mask(y, ss, sn, sz=None, mask_type="irm1", mod=None, ts=None, **kwargs):
-    """tango.py:189-225, oracle branches ('irmX' / 'ibmX' / 'iamX' / 'ivad')."""
+    """tango.py:189-225: oracle masks ('irmX' / 'ibmX' / 'iamX' / 'ivad') or the mask a network predicts
+    ('crnn' / 'rnn': `mod` on the device through disco_b200.dnn_mask, window keywords win_len / win_hop /
+    frame_to_pred as in the reference).  Returns an (F, T) array like the reference."""
     if mask_type[:-1] in ("irm", "ibm", "iam"):
         return tf_mask(ss, sn, type=mask_type)
-    if "rnn" in mask_type:
-        raise NotImplementedError("DNN mask estimation is the next row of the scope table (SURVEY.md 8 f-1)")
+    if "rnn" in mask_type:                                   # tango.py:209-215
+        from .. import dnn_mask
+        if mask_type != "crnn":
+            raise NotImplementedError("only the 3-D ('crnn') input arrangement of prepare_data is implemented")
+        kw = {k: kwargs[k] for k in ("win_len", "win_hop", "frame_to_pred", "norm_type") if k in kwargs}
+        m = dnn_mask.estimate_mask(mod, y, sz, device=DEVICE, **kw)            # (T, F) on the device
+        return m.T.cpu().numpy()
     if mask_type == "ivad":
         m = np.zeros(np.shape(ss))
         vad = vad_oracle_batch(ts, win_len=N_FFT, win_hop=N_HOP)[::N_HOP]

@@ -533,7 +533,15 @@ int disco_transpose_f32(const float* in, float* out, int batch, int rows, int co
 }
 int disco_apply_mask(const void* in, const float* m, void* out, size_t n_elem, int one_minus, void* stream) {
     if (!in || !m || !out) return fail(DISCO_ERR_INVALID, "null pointer");
-    CU(launch_apply_mask((const float2*)in, m, (float2*)out, n_elem, one_minus, (cudaStream_t)stream),
+    CU(launch_apply_mask((const float2*)in, m, (float2*)out, n_elem, n_elem, 1, one_minus, (cudaStream_t)stream),
+       "apply_mask launch");
+    return 0;
+}
+int disco_apply_mask_channels(const void* in, const float* m, void* out, size_t n_grp, int chans, size_t plane,
+                              int one_minus, void* stream) {
+    if (!in || !m || !out || chans < 1) return fail(DISCO_ERR_INVALID, "bad arguments");
+    CU(launch_apply_mask((const float2*)in, m, (float2*)out, n_grp * chans * plane, plane, chans, one_minus,
+                         (cudaStream_t)stream),
        "apply_mask launch");
     return 0;
 }

@@ -167,8 +167,9 @@ cudaError_t launch_tf_mask(const float2* S, const float2* Nn, float* M, size_t n
 // out[b][c][r] = in[b][r][c]
 cudaError_t launch_transpose_c64(const float2* in, float2* out, int batch, int rows, int cols, cudaStream_t st);
 cudaError_t launch_transpose_f32(const float* in, float* out, int batch, int rows, int cols, cudaStream_t st);
-// out = m * in or (1 - m) * in, elementwise over [n][T*F]; mask broadcast per group
-cudaError_t launch_apply_mask(const float2* in, const float* m, float2* out, size_t n, int one_minus,
-                              cudaStream_t st);
+// out = m * in or (1 - m) * in over n = n_grp * chans * plane points; the mask [n_grp][plane] is shared by the
+// `chans` channels of a group
+cudaError_t launch_apply_mask(const float2* in, const float* m, float2* out, size_t n, size_t plane, int chans,
+                              int one_minus, cudaStream_t st);
 
 }  // namespace disco

@@ -70,18 +70,21 @@ cudaError_t launch_transpose_f32(const float* in, float* out, int batch, int row
     return launch_transpose<float>(in, out, batch, rows, cols, st);
 }
 
+// out = m * in (or (1 - m) * in); the mask plane of a group is shared by its `chans` channels:
+// in / out [n_grp][chans][plane], m [n_grp][plane]
 __global__ void apply_mask_kernel(const float2* __restrict__ in, const float* __restrict__ m,
-                                  float2* __restrict__ out, size_t n, int one_minus) {
+                                  float2* __restrict__ out, size_t n, size_t plane, int chans, int one_minus) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float w = m[i];
+    const size_t mi = chans == 1 ? i : (i / (plane * chans)) * plane + i % plane;
+    float w = m[mi];
     if (one_minus) w = 1.f - w;
     out[i] = cscale(in[i], w);
 }
-cudaError_t launch_apply_mask(const float2* in, const float* m, float2* out, size_t n, int one_minus,
-                              cudaStream_t st) {
+cudaError_t launch_apply_mask(const float2* in, const float* m, float2* out, size_t n, size_t plane, int chans,
+                              int one_minus, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    apply_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, m, out, n, one_minus);
+    apply_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, m, out, n, plane, chans, one_minus);
     return cudaGetLastError();
 }
 

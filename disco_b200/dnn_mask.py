@@ -20,6 +20,7 @@ State-dict keys are identical to the reference's CRNN (``cnn.model.{0,1,3,4,6,7}
 ``rnn.model.0.rnn_layer.*``, ``ff.layers.0.*``), so trained checkpoints load unchanged
 (tango.py:133-134 ``model.load_state_dict(saved_weights['model_state_dict'])``).
 """
+import contextlib
 import math
 
 import numpy as np
@@ -211,12 +212,35 @@ def reshape_mask_device(m_stack, output_frame="last"):
     raise ValueError(":param output_frame: should be either 'last', 'all' or 'mid'")
 
 
+@contextlib.contextmanager
+def fp32_exact(on=True):
+    """Inside: cuDNN convolutions and cuBLAS matmuls in IEEE float32 (PyTorch's default lets cuDNN use TF32,
+    whose 10-bit mantissa moves the sigmoid outputs by ~1e-4 -- more than the beamformer's parity budget)."""
+    if not on:
+        yield
+        return
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 @torch.no_grad()
 def estimate_mask(mod, y_spec, z_specs=None, win_len=21, win_hop=1, frame_to_pred="mid", norm_type=None,
-                  device="cuda", exact=False):
+                  device="cuda", exact=True):
     """get_mask(..., mask_type='crnn') of tango.py:209-215, on the device.
     y_spec (F, T) mixture STFT (or magnitude) of the reference microphone, z_specs list of (F, T) compressed
-    signals of the other nodes (step 2).  Returns the mask FRAME-MAJOR (T, F) float32, ready for the kernels."""
+    signals of the other nodes (step 2).  Returns the mask FRAME-MAJOR (T, F) float32, ready for the kernels.
+    exact=True (default) runs the network in IEEE float32 like the reference's CPU path; exact=False leaves
+    PyTorch's TF32 defaults on (faster convolutions, masks within ~3e-4)."""
+    with fp32_exact(exact):
+        return _estimate_mask(mod, y_spec, z_specs, win_len, win_hop, frame_to_pred, norm_type, device)
+
+
+def _estimate_mask(mod, y_spec, z_specs, win_len, win_hop, frame_to_pred, norm_type, device):
     mod.eval()
     frames_lost = int(win_len - mod.get_loss_frames("last")[-1][-1])
     x = _stack_inputs(y_spec, z_specs, norm_type, device)

@@ -513,11 +513,18 @@ def transpose_last2(a):
 
 @_on_device
 def apply_mask(X, m, one_minus=False):
-    """m * X or (1 - m) * X elementwise (same shapes), complex64 x float32."""
+    """m * X or (1 - m) * X, complex64 x float32.  Same shapes, or X [..., C, T, F] with one mask plane
+    m [..., T, F] shared by the C channels of a group (one launch either way)."""
     _need(X, torch.complex64, "X")
     _need(m, torch.float32, "m")
-    if X.shape != m.shape:
-        raise ValueError("shape mismatch")
     out = torch.empty_like(X)
-    _lib.check(_lib.load().disco_apply_mask(_ptr(X), _ptr(m), _ptr(out), X.numel(), 1 if one_minus else 0, _stream()))
+    lib = _lib.load()
+    if X.shape == m.shape:
+        _lib.check(lib.disco_apply_mask(_ptr(X), _ptr(m), _ptr(out), X.numel(), 1 if one_minus else 0, _stream()))
+    elif X.dim() == m.dim() + 1 and tuple(X.shape[:-3]) + tuple(X.shape[-2:]) == tuple(m.shape):
+        plane = X.shape[-1] * X.shape[-2]
+        _lib.check(lib.disco_apply_mask_channels(_ptr(X), _ptr(m), _ptr(out), m.numel() // plane, X.shape[-3], plane,
+                                                 1 if one_minus else 0, _stream()))
+    else:
+        raise ValueError("shape mismatch")
     return out

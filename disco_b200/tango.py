@@ -35,24 +35,19 @@ def _ref_plane(X, ref):
 
 
 def _bcast_mask(X, m, one_minus):
-    """m (or 1 - m) [B, K, T, F] applied to every channel of X [B, K, C, T, F]."""
-    out = torch.empty_like(X)
-    for c in range(X.shape[2]):
-        out[:, :, c] = ops.apply_mask(X[:, :, c].contiguous(), m, one_minus)
-    return out
+    """m (or 1 - m) [B, K, T, F] applied to every channel of X [B, K, C, T, F] (one launch)."""
+    return ops.apply_mask(X, m, one_minus)
 
 
 def _ivad_mask(s_ref, n_fft):
     """'ivad' masks (tango.py:216-221): the per-sample energy VAD of the clean reference channel,
-    taken every hop and spread over all bins.  s_ref [B, K, L] -> [B, K, T, F] float32 (0/1)."""
-    from .compat.sigproc_utils import vad_oracle_batch_device
+    taken every hop and spread over all bins.  s_ref [B, K, L] -> [B, K, T, F] float32 (0/1); all (b, k) at once."""
+    from .compat.sigproc_utils import vad_oracle_rows_device
     B, K, L = s_ref.shape
     hop, F, T = n_fft // 2, n_fft // 2 + 1, ops.n_frames(L, n_fft)
+    vad = vad_oracle_rows_device(s_ref.reshape(B * K, L), win_len=n_fft, win_hop=hop)[:, ::hop]      # [B*K, <= T]
     out = torch.zeros((B, K, T, F), dtype=torch.float32, device=s_ref.device)
-    for b in range(B):
-        for k in range(K):
-            vad = vad_oracle_batch_device(s_ref[b, k], win_len=n_fft, win_hop=hop)[::hop]
-            out[b, k, :vad.numel(), :] = vad.to(torch.float32)[:, None]
+    out[:, :, :vad.shape[1], :] = vad.to(torch.float32).view(B, K, -1, 1)
     return out
 
 
@@ -271,9 +266,7 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
     uniform = len(set(chans)) == 1
     use_dnn = masks is None and any("rnn" in v for v in vads)
-    if use_dnn:
-        if not uniform:
-            raise NotImplementedError("DNN masks with ragged channel counts")
+    if use_dnn and uniform:
         return _offline_tango_dnn(y, s, n, vads, mods, mask_for_z, z_sigs, n_fft, mu, filter_type, rank,
                                   torch.device(device))
     dev = torch.device(device)
@@ -290,7 +283,8 @@ def offline_tango(y, s, n, vads="irm1", mods=None, mask_for_z="local", z_sigs="z
                             rank=rank, out_layout="FT")
         res = {k: v[0].cpu().numpy() for k, v in res.items()}
     else:
-        res = _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask)
+        res = _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask,
+                                    mods=mods, z_sigs=z_sigs)
     is_bool = [masks is None and "ibm" in v for v in vads]
     is_f64 = [masks is None and v == "ivad" for v in vads]       # the reference's VAD masks are float64
     out = []
@@ -348,43 +342,97 @@ def _offline_tango_dnn(y, s, n, vads, mods, mask_for_z, z_sigs, n_fft, mu, filte
     return tuple([res[nm][k] for k in range(K)] for nm in OUTPUT_NAMES)
 
 
-def _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask):
+def _offline_tango_ragged(y, s, n, vads, mask_for_z, n_fft, mu, filter_type, rank, masks, dev, to_mask,
+                          mods=None, z_sigs="zs_hat"):
     """Nodes with different microphone counts (reference tango.py:259-260, 284): step 1 and step 2 run
-    once per channel count on the nodes that have it; Z always holds all K nodes."""
-    if mask_for_z != "local":
-        raise NotImplementedError("ragged channel counts are supported for mask_for_z='local'")
+    once per channel count on the nodes that have it; Z (and the signals the other nodes contribute to the
+    step-2 statistics under every `mask_for_z` mode, tango.py:396-429) always hold all K nodes.
+    Masks: oracle types, externally supplied `masks`, or DNN masks (`mods`, tango.py:209-215) -- the estimators only
+    see the reference microphone and the compressed signals, so they do not care about the channel counts."""
+    if mask_for_z == "use_oracle_sigs":
+        raise NotImplementedError("'use_oracle_sigs' is ill-formed in the reference (tango.py:423-427 "
+                                  "indexes per-channel arrays by node)")
     K = len(y)
     L = len(y[0][0])
     T, F = ops.n_frames(L, n_fft), n_fft // 2 + 1
+    dnn = masks is None and any("rnn" in v for v in vads)
+    if dnn:
+        from . import dnn_mask
+        dkw = dict(win_len=21, win_hop=1, frame_to_pred="mid", device=dev)
+    spec_ft = lambda a: a.transpose(-1, -2)
     groups = {}
     for k in range(K):
         groups.setdefault(len(y[k]), []).append(k)
-    Z = torch.empty((1, K, T, F), dtype=torch.complex64, device=dev)
-    Zs, Zn_ = torch.empty_like(Z), torch.empty_like(Z)
-    ZN = torch.empty_like(Z)
+    cplx = lambda: torch.empty((1, K, T, F), dtype=torch.complex64, device=dev)
+    Z, Zs, Zn_, ZN, Sref, Nref, Yref = cplx(), cplx(), cplx(), cplx(), cplx(), cplx(), cplx()
     MZ = torch.empty((1, K, T, F), dtype=torch.float32, device=dev)
     MW = torch.empty_like(MZ)
+    use_osn = "use_oracle_" in mask_for_z
     keep = {}
+    # ---- step 1 per channel count
     for C, nodes in sorted(groups.items()):
         yd, sd, nd = _to_dev(y, nodes, dev), _to_dev(s, nodes, dev), _to_dev(n, nodes, dev)
         S, N = ops.stft(sd, n_fft), ops.stft(nd, n_fft)
-        if masks is None:
-            om = lambda kind: _ivad_mask(sd[:, :, 0], n_fft) if kind == "ivad" else \
-                ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), kind)
-            mz = om(vads[0])
-            mw = mz if vads[1] == vads[0] else om(vads[1])
+        idx = torch.tensor(nodes, device=dev)
+        Sref[0, idx], Nref[0, idx] = S[0, :, 0], N[0, :, 0]
+
+        def om(kind):
+            if kind == "ivad":
+                return _ivad_mask(sd[:, :, 0], n_fft)
+            return ops.tf_mask(_ref_plane(S, 0), _ref_plane(N, 0), kind)
+        if masks is not None:
+            mz = to_mask(masks[0], nodes)
+        elif "rnn" in vads[0]:
+            Yr = ops.stft(yd[:, :, 0].contiguous(), n_fft)
+            mz = torch.stack([dnn_mask.estimate_mask(mods[0], spec_ft(Yr[0, i]), None, **dkw)
+                              for i in range(len(nodes))])[None]
         else:
-            mz, mw = to_mask(masks[0], nodes), to_mask(masks[1], nodes)
-        st1 = tango_step1(yd, mz, n_fft, mu, filter_type, rank, 0)
+            mz = om(vads[0])
+        st1 = tango_step1(yd, mz, n_fft, mu, filter_type, rank, 0, oracle_sn=(S, N) if use_osn else None)
         zs = ops.filter_sum(st1["W1"], S, None, conj=True, n_fft=n_fft)
         zn_ = ops.filter_sum(st1["W1"], N, None, conj=True, n_fft=n_fft)
-        idx = torch.tensor(nodes, device=dev)
         Z[0, idx], Zs[0, idx], Zn_[0, idx], ZN[0, idx] = st1["z_y"][0], zs[0], zn_[0], st1["zn"][0]
-        MZ[0, idx], MW[0, idx] = mz[0], mw[0]
-        keep[C] = (nodes, st1["Y"], S, N, mw)
+        Yref[0, idx] = st1["Y"][0, :, 0]
+        MZ[0, idx] = mz[0]
+        keep[C] = (nodes, st1["Y"], S, N, om)
+    # ---- step-2 masks (tango.py:387-394)
+    for C, (nodes, Y, S, N, om) in sorted(keep.items()):
+        idx = torch.tensor(nodes, device=dev)
+        if masks is not None:
+            MW[0, idx] = to_mask(masks[1], nodes)[0]
+        elif "rnn" in vads[1]:
+            if mods[1] is None:
+                MW[0, idx] = MZ[0, idx]
+            else:
+                for k in nodes:
+                    others = [j for j in range(K) if j != k]
+                    if z_sigs in ("zs_hat", "zn_hat"):
+                        zin = Z if z_sigs == "zs_hat" else ZN
+                        zl = [spec_ft(zin[0, j]) for j in others]
+                    else:
+                        zl = [spec_ft(t[0, j]) for j in others for t in (Z, ZN)]
+                    MW[0, k] = dnn_mask.estimate_mask(mods[1], spec_ft(Yref[0, k]), zl, **dkw)
+        else:
+            MW[0, idx] = (MZ[0, idx] if vads[1] == vads[0] else om(vads[1])[0])
+    # ---- what the other nodes contribute to the step-2 statistics (tango.py:396-429)
+    z_rs = z_rn = None
+    if mask_for_z == "distant":
+        z_rs, z_rn = ops.apply_mask(Z, MW, False), ops.apply_mask(Z, MW, True)
+    elif mask_for_z == "compressed":
+        mc = ops.tf_mask(Zs, Zn_, vads[0])
+        z_rs, z_rn = ops.apply_mask(Z, mc, False), ops.apply_mask(Z, mc, True)
+    elif mask_for_z == "use_oracle_refs":
+        z_rs, z_rn = Sref, Nref
+    elif mask_for_z == "use_oracle_zs":
+        z_rs, z_rn = Zs, Zn_
+    elif mask_for_z != "local":              # 'previous' and any other string: unmasked z in both statistics
+        z_rs = z_rn = Z
+    # ---- step 2 per channel count
     res = {nm: np.empty((K, F, T), np.complex64) for nm in ("yf", "sf", "nf")}
-    for C, (nodes, Y, S, N, mw) in sorted(keep.items()):
-        yf, W2 = tango_step2(Y, Z, mw, n_fft, mu, filter_type, rank, "FT", node_sel=nodes)
+    for C, (nodes, Y, S, N, om) in sorted(keep.items()):
+        idx = torch.tensor(nodes, device=dev)
+        mw = MW[:, idx].contiguous()
+        yf, W2 = tango_step2(Y, Z, mw, n_fft, mu, filter_type, rank, "FT", node_sel=nodes, z_rs=z_rs, z_rn=z_rn)
         sf = ops.filter_sum(W2, S, Zs, conj=True, n_fft=n_fft, out_layout="FT", node_sel=nodes)
         nf = ops.filter_sum(W2, N, Zn_, conj=True, n_fft=n_fft, out_layout="FT", node_sel=nodes)
         for i, k in enumerate(nodes):

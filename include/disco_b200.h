@@ -240,6 +240,10 @@ DISCO_API int disco_transpose_c64(const void* in, void* out, int batch, int rows
 DISCO_API int disco_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream);
 /* out = m * in (one_minus = 0) or (1 - m) * in (one_minus = 1), elementwise (tango.py:397-398, 402-403) */
 DISCO_API int disco_apply_mask(const void* in, const float* m, void* out, size_t n_elem, int one_minus, void* stream);
+/* The same with one mask plane per group shared by its `chans` channels (s_hat_w / n_hat_w of every microphone of a
+ * node under the node's mask_w, reference tango.py:413-414): in, out [n_grp][chans][plane], m [n_grp][plane]. */
+DISCO_API int disco_apply_mask_channels(const void* in, const float* m, void* out, size_t n_grp, int chans, size_t plane,
+                              int one_minus, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,10 @@ TANGO_CASES = {
     # single node, two DIFFERENT masks: the two-mask fused route (stft_scm2 + filter_dual) against the reference
     "tango_k1c4_irm1_irm2": (14, [4], 16000, ("irm1", "irm2"), "local", ("yf", "z_y", "zn")),
     "tango_k1c3_iam1_irm1": (15, [3], 7000, ("iam1", "irm1"), "local", ("yf", "z_y", "zn")),
+    # ragged channel counts under the other mask_for_z modes (tango.py:396-429)
+    "tango_k3_ragged_distant": (16, [2, 3, 2], 6000, ("irm1", "irm1"), "distant", ("yf", "z_y")),
+    "tango_k3_ragged_compressed": (17, [3, 1, 2], 6000, ("irm1", "irm2"), "compressed", ("yf", "z_y")),
+    # (ragged + 'use_oracle_refs' raises inside the reference: np.array(s_stft) of ragged lists, tango.py:405)
 }
 NAMES = ("yf", "sf", "nf", "z_y", "z_s", "z_n", "zn", "masks_z", "mask_w")
 
