@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--shard", default="utterances", choices=["utterances", "nodes"])
     ap.add_argument("--masks", default="oracle", choices=["oracle", "crnn"],
                     help="e2e leg: masks uploaded from the host (oracle) or predicted on device by the reference CRNN")
+    ap.add_argument("--crnn-exact", action="store_true", help="run the CRNN in IEEE float32 (default: TF32)")
     args = ap.parse_args()
     B, K, C, L, n_fft, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -571,8 +572,8 @@ def main():
     if not args.no_e2e:
         yf_host = torch.empty((B, K, T, F), dtype=torch.complex64).pin_memory()
         if args.masks == "crnn" and K == 1:
-            from bench_e2e_crnn import CrnnPipeline
-            pipe = CrnnPipeline(B, C, L, n_fft, args.e2e_chunks, dev)
+            from disco_b200.plan import CrnnTangoPipeline
+            pipe = CrnnTangoPipeline(B, C, L, n_fft, args.e2e_chunks, dev, exact=args.crnn_exact)
             y_i16 = pipe.to_pcm(y_host)
 
             def e2e_step():   # int16 PCM H2D -> CRNN masks on device -> the whole path -> D2H of yf

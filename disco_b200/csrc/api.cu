@@ -15,6 +15,22 @@
 
 using namespace disco;
 
+namespace disco {
+// SM count of the CURRENT device (cached per device: processes may drive several GPUs)
+int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+}  // namespace disco
+
 namespace {
 
 thread_local std::string g_err;
@@ -78,19 +94,6 @@ int get_tables(int n_fft, Tables* out) {
     g_tables[key] = t;
     *out = t;
     return 0;
-}
-
-// SM count of the CURRENT device (cached per device: processes may drive several GPUs)
-int sm_count() {
-    static int cache[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cache[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cache[dev] = n;
-    }
-    return cache[dev];
 }
 
 // Persistent launch geometry of the fused STFT kernel: one CTA per SM (fewer when there are fewer tiles).
@@ -270,6 +273,7 @@ int disco_masked_scm(const void* Y, const void* Z, const float* mask, int mask_l
     int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel, z_layout);
     if (rc) return rc;
     if (!Rss || !Rnn) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (a.in.n_grp > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 (utterance, node) groups per call");
     a.mask = mask;
     a.mask_ft = (mask_layout == DISCO_LAYOUT_FT);
     a.Rss = (float2*)Rss;
@@ -395,6 +399,7 @@ int disco_filter_sum(const void* W, int conj_w, const void* Y, const void* Z, vo
     if (rc) return rc;
     if (!W || !out) return fail(DISCO_ERR_INVALID, "null pointer");
     if (ref < 0 || ref >= C + K - 1) return fail(DISCO_ERR_INVALID, "ref channel out of range");
+    if (a.in.n_grp > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 (utterance, node) groups per call");
     a.W = (const float2*)W;
     a.conj_w = conj_w;
     a.out = (float2*)out;
@@ -455,6 +460,7 @@ int disco_scm_recursive(const void* Y, const void* Z, const float* mask, const v
     int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
     if (rc) return rc;
     if (C + K - 1 > 8) return fail(DISCO_ERR_UNSUPPORTED, "recursive SCM: C + K - 1 must be <= 8");
+    if (a.in.n_grp > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 (utterance, node) groups per call");
     if (!Rss || !Rnn || (!R0ss) != (!R0nn)) return fail(DISCO_ERR_INVALID, "null pointer");
     if (block < 1 || block > 64) return fail(DISCO_ERR_INVALID, "block must be 1..64 frames");
     if (!(lambda_cor >= 0.0 && lambda_cor < 1.0)) return fail(DISCO_ERR_INVALID, "lambda_cor must be in [0, 1)");
@@ -486,6 +492,7 @@ int disco_filter_sum_blocks(const void* W, int conj_w, const void* Y, const void
     int rc = make_cat(&a.in, Y, Z, n_utt, K, C, T, n_fft, node_sel, n_sel);
     if (rc) return rc;
     if (C + K - 1 > 8) return fail(DISCO_ERR_UNSUPPORTED, "block filter: C + K - 1 must be <= 8");
+    if (a.in.n_grp > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 (utterance, node) groups per call");
     if (!W || !out) return fail(DISCO_ERR_INVALID, "null pointer");
     if (block < 1 || block > 64 || lag < 0) return fail(DISCO_ERR_INVALID, "bad block / lag");
     if (ref < 0 || ref >= C + K - 1) return fail(DISCO_ERR_INVALID, "ref channel out of range");
@@ -522,12 +529,14 @@ int disco_band_stats(const float* x, const float* sel, const double* ba, double*
 
 int disco_transpose_c64(const void* in, void* out, int batch, int rows, int cols, void* stream) {
     if (!in || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (batch > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 planes per call");
     CU(launch_transpose_c64((const float2*)in, (float2*)out, batch, rows, cols, (cudaStream_t)stream),
        "transpose launch");
     return 0;
 }
 int disco_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream) {
     if (!in || !out) return fail(DISCO_ERR_INVALID, "null pointer");
+    if (batch > kMaxGridYZ) return fail(DISCO_ERR_UNSUPPORTED, "at most 65535 planes per call");
     CU(launch_transpose_f32(in, out, batch, rows, cols, (cudaStream_t)stream), "transpose launch");
     return 0;
 }

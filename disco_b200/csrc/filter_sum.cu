@@ -176,7 +176,7 @@ static cudaError_t launch_d(const FilterArgs& a, cudaStream_t st) {
     const int fblocks = (a.in.F + 31) / 32;
     // enough CTAs to fill the machine: split time into slabs (multiples of 32 frames) when groups are few
     int slabs = 1;
-    const int want = 148 * 4;
+    const int want = sm_count() * 4;
     while (fblocks * a.in.n_grp * slabs < want && (a.in.T + slabs - 1) / slabs > 64) slabs *= 2;
     int fps = ((a.in.T + slabs - 1) / slabs + 31) / 32 * 32;
     slabs = (a.in.T + fps - 1) / fps;

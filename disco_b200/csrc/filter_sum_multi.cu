@@ -114,7 +114,7 @@ static cudaError_t launch_fsm(const FilterArgs& a, cudaStream_t st) {
     // enough CTAs for ~8 waves of the resident slots (equal-sized CTAs: few waves quantise badly), at least 8 tiles each
     const int nblk = (a.in.F + 31) / 32, B = a.in.n_grp / K;
     const int by_smem = (int)((227 * 1024) / (G::SMEM + 1024));
-    const int slots = 148 * (by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem));
+    const int slots = sm_count() * (by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem));
     int nseg = (8 * slots + nblk * B - 1) / (nblk * B);
     const int max_seg = (a.in.T / G::TS + 7) / 8;
     nseg = nseg < 1 ? 1 : (nseg > max_seg ? (max_seg < 1 ? 1 : max_seg) : nseg);

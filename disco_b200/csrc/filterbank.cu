@@ -94,7 +94,7 @@ cudaError_t launch_band_stats(const BankArgs& a, int order, cudaStream_t st) {
     // bands per CTA: as few as needed to give every SM a CTA, at most all of them
     const int sig_blocks = (a.n_sig + 31) / 32;
     int bands_per_cta = a.n_band < kBankWarps ? a.n_band : kBankWarps;
-    while (bands_per_cta > 1 && sig_blocks * ((a.n_band + bands_per_cta - 1) / bands_per_cta) < 148) --bands_per_cta;
+    while (bands_per_cta > 1 && sig_blocks * ((a.n_band + bands_per_cta - 1) / bands_per_cta) < sm_count()) --bands_per_cta;
     dim3 grid(sig_blocks, (a.n_band + bands_per_cta - 1) / bands_per_cta);
     const int threads = 32 * bands_per_cta;
     switch (order) {

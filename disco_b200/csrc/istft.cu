@@ -165,7 +165,7 @@ static cudaError_t launch_n(const IstftArgs& a, cudaStream_t st) {
     if (T_eff < 1) return cudaErrorInvalidValue;
     const int pairs = (a.n_sig + 1) / 2;
     int chunks = 1;
-    while (pairs * chunks < 148 * 2 && (T_eff + chunks - 1) / chunks > 4 * G::ITEMS) chunks *= 2;
+    while (pairs * chunks < sm_count() * 2 && (T_eff + chunks - 1) / chunks > 4 * G::ITEMS) chunks *= 2;
     int fpc = ((T_eff + chunks - 1) / chunks + G::ITEMS - 1) / G::ITEMS * G::ITEMS;
     chunks = (T_eff + fpc - 1) / fpc;
     const size_t smem = (size_t)G::ITEMS * G::ROW * sizeof(float2) + H * sizeof(float2) + N * sizeof(float2) +

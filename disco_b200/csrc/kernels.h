@@ -5,6 +5,11 @@
 
 namespace disco {
 
+// SM count of the current device (cached per device; api.cu) -- launch heuristics size their grids with it
+int sm_count();
+// grid.y / grid.z are limited to 65535 blocks
+constexpr int kMaxGridYZ = 65535;
+
 struct StftArgs {
     const float* x;         // [n_sig][L] float32 time signals (n_sig = n_grp * C, last group may be short)
     const float* mask;      // SCM only: [n_grp][T][F] (mask_ft = 0) or [n_grp][F][T] (mask_ft = 1)

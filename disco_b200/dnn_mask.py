@@ -178,6 +178,35 @@ class CRNN(nn.Module):
             out.append(self._head(w))
         return torch.cat(out, 0)
 
+    @torch.no_grad()
+    def forward_batch(self, x, frame_to_pred="mid", chunk=8192):
+        """A whole batch of padded spectrograms at once: x [B, n_ch, F, T_padded] -> masks [B, n_samples, n_freq]
+        (frame-major, float32), equal to reshape_mask(forward(windows), frame_to_pred) for every utterance.
+        The CNN runs once per batch; the recurrent layers only run up to the predicted frame of each window (the
+        later steps of a unidirectional GRU cannot influence it) and the output layer only on that frame --
+        8 of 15 steps and 1 of 15 frames for the reference's 'mid' (tango.py:34-35)."""
+        B = x.shape[0]
+        win_len = self.input_shape[1]
+        feats = self.cnn(x.permute(0, 1, 3, 2))                          # [B, C, T_padded - (win_len - x_out), f_out]
+        Cc, Tf, fo = feats.shape[1:]
+        n = Tf - self.x_out + 1
+        assert n == 1 + (x.shape[3] - win_len)
+        if frame_to_pred == "mid":
+            last = int(math.floor(self.x_out / 2))                       # reshape_mask: floor(w/2) : ceil(w/2)
+        elif frame_to_pred == "last":
+            last = self.x_out - 1
+        else:
+            raise NotImplementedError("forward_batch predicts the 'mid' or the 'last' frame")
+        win = feats.unfold(2, self.x_out, 1)                             # [B, C, n, f_out, x_out] (view)
+        out = torch.empty((B, n, self.ff.layers[-1].out_features), dtype=feats.dtype, device=feats.device)
+        per = max(1, chunk // max(1, n))
+        for b0 in range(0, B, per):                                      # bound the unfolded copy
+            w = win[b0:b0 + per].permute(0, 2, 1, 4, 3).contiguous()     # (b, n, C, x_out, f_out)
+            w = w.view(-1, self.x_out, Cc * fo)[:, :last + 1]            # the reference's literal re-view (crnn.py:59)
+            h = self.rnn(w.contiguous())[:, last]                        # hidden state at the predicted frame
+            out[b0:b0 + per] = self.ff(h).view(-1, n, out.shape[-1])
+        return out
+
     def get_loss_frames(self, output_frames):
         """crnn.py:65-87."""
         win_in, win_out = self.input_shape[1], self.x_out
@@ -238,6 +267,19 @@ def estimate_mask(mod, y_spec, z_specs=None, win_len=21, win_hop=1, frame_to_pre
     PyTorch's TF32 defaults on (faster convolutions, masks within ~3e-4)."""
     with fp32_exact(exact):
         return _estimate_mask(mod, y_spec, z_specs, win_len, win_hop, frame_to_pred, norm_type, device)
+
+
+@torch.no_grad()
+def estimate_masks_batch(mod, Y_ref, win_len=21, frame_to_pred="mid", exact=True):
+    """Masks of a whole batch in a few launches: Y_ref [B, T, F] complex64 / float32 device tensor (frame-major
+    STFT of the reference microphone of single-node arrays, no compressed signals) -> [B, T, F] float32.
+    Same numbers as estimate_mask() per utterance (prepare_data's clipping and zero padding, tango.py:209-215)."""
+    mod.eval()
+    frames_lost = int(win_len - mod.get_loss_frames("last")[-1][-1])
+    x = Y_ref.abs().clamp(STFT_MIN, STFT_MAX).to(torch.float32).transpose(-1, -2).unsqueeze(1)     # [B, 1, F, T]
+    x = torch.nn.functional.pad(x, get_frames_to_pad(win_len, frame_to_pred, out_len=win_len - frames_lost))
+    with fp32_exact(exact):
+        return mod.forward_batch(x, frame_to_pred)
 
 
 def _estimate_mask(mod, y_spec, z_specs, win_len, win_hop, frame_to_pred, norm_type, device):

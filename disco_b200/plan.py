@@ -120,3 +120,67 @@ class TangoPipeline:
                 plan.store("yf", yf_host[lo:hi])
         for st in self.streams:
             cur.wait_stream(st)
+
+
+class CrnnTangoPipeline:
+    """The literal deployment chain of BASELINE configs[1] for single-node arrays, host to host: int16 PCM in pinned
+    host memory -> device (half the bytes of float32; the conversion x / 32768 is exactly what soundfile's
+    dtype='float32' read does, reference tango.py:95-100) -> |STFT| of the reference microphone -> the reference's
+    CRNN mask estimators on the device (dnn_mask.estimate_masks_batch; tango.py:209-215) -> two-mask fused
+    STFT+SCM, both solves, one-pass dual filter (captured CUDA graph) -> beamformed STFT back to the host.
+    Only the signals cross PCIe on the way in.  The batch is cut into `chunks` slices on separate streams so
+    upload, mask estimation, beamforming and download of different slices overlap."""
+
+    def __init__(self, B, C, L, n_fft=512, chunks=4, device=None, models=None, exact=False, seed=0):
+        from . import dnn_mask
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.B, self.C, self.L, self.n_fft, self.exact = B, C, L, n_fft, exact
+        chunks = max(1, min(chunks, B))
+        self.splits = [((B * i) // chunks, (B * (i + 1)) // chunks) for i in range(chunks)]
+        if models is None:           # randomly initialised networks of the reference architecture (tango.py:127-132)
+            torch.manual_seed(seed)
+            models = (dnn_mask.CRNN(1), dnn_mask.CRNN(1))
+        self.models = tuple(m.to(self.device).eval() for m in models)
+        self.plans = [TangoGraph(hi - lo, 1, C, L, n_fft=n_fft, chunks=1, device=self.device) for lo, hi in self.splits]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.splits]
+        self.pcm = [torch.empty((hi - lo, 1, C, L), dtype=torch.int16, device=self.device) for lo, hi in self.splits]
+        self.ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in self.splits]
+        self.how = ("CrnnTangoPipeline: %d batch slices; per slice int16 H2D -> x/32768 -> STFT(ref mic) -> 2 CRNNs (%s) -> "
+                    "graph replay -> D2H" % (chunks, "IEEE fp32" if exact else "TF32 convolutions / matmuls"))
+
+    @staticmethod
+    def to_pcm(y_host):
+        """float32 [-1, 1) signals -> int16 PCM (pinned), what a 16-bit wav file holds."""
+        return (y_host.clamp(-1.0, 32767.0 / 32768.0) * 32768.0).round().to(torch.int16).pin_memory()
+
+    def process(self, pcm_host, yf_host):
+        """pcm_host [B, 1, C, L] int16 pinned, yf_host [B, 1, T, F] complex64 pinned."""
+        from . import dnn_mask
+        cur = torch.cuda.current_stream(self.device)
+        for i, ((lo, hi), plan, st) in enumerate(zip(self.splits, self.plans, self.streams)):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                e = self.ev[i]
+                e[0].record(st)
+                self.pcm[i].copy_(pcm_host[lo:hi], non_blocking=True)
+                torch.mul(self.pcm[i], 1.0 / 32768.0, out=plan.y)          # exact: a power of two
+                e[1].record(st)
+                Yref = ops.stft(plan.y[:, 0, 0].contiguous(), self.n_fft)  # [Bc, T, F]
+                plan.mask_z[:, 0] = dnn_mask.estimate_masks_batch(self.models[0], Yref, exact=self.exact)
+                plan.mask_w[:, 0] = dnn_mask.estimate_masks_batch(self.models[1], Yref, exact=self.exact)
+                e[2].record(st)
+                plan.run()
+                e[3].record(st)
+                plan.store("yf", yf_host[lo:hi])
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def report(self):
+        """Mean per-slice times of the last process() call (call after a device synchronisation)."""
+        up = [e[0].elapsed_time(e[1]) for e in self.ev]
+        nn = [e[1].elapsed_time(e[2]) for e in self.ev]
+        bf = [e[2].elapsed_time(e[3]) for e in self.ev]
+        return {"slices": len(self.ev), "upload_convert_ms_per_slice": sum(up) / len(up),
+                "crnn_ms_per_slice": sum(nn) / len(nn), "beamform_ms_per_slice": sum(bf) / len(bf),
+                "crnn_ms_per_batch": sum(nn), "precision": "ieee fp32" if self.exact else "tf32",
+                "models": "2 x reference CRNN (517,729 parameters each), random weights"}

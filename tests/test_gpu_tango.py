@@ -224,6 +224,36 @@ def test_host_pipeline_matches_eager(dev):
     assert torch.equal(out, ref["yf"].cpu())
 
 
+def test_crnn_pipeline_matches_manual_chain(dev):
+    """CrnnTangoPipeline (int16 PCM host -> device -> CRNN masks -> two-mask fused path -> host) == the same chain
+    spelled out with the per-utterance mask estimator and tango_batched."""
+    from disco_b200 import dnn_mask, ops
+    from disco_b200.plan import CrnnTangoPipeline
+    from disco_b200.synth import make_batch
+    from disco_b200.tango import tango_batched
+    B, C, L = 3, 2, 16000
+    T, F = 1 + L // 256, 257
+    torch.manual_seed(5)
+    models = (dnn_mask.CRNN(1, cnn_filters=(4, 6, 6), rnn_units=(8,)), dnn_mask.CRNN(1, cnn_filters=(4, 6, 6), rnn_units=(8,)))
+    pipe = CrnnTangoPipeline(B, C, L, chunks=2, device=dev, models=models, exact=True)
+    y, _, _ = make_batch(B, 1, C, L, seed0=900)
+    pcm = pipe.to_pcm(torch.from_numpy(y))
+    out = torch.empty((B, 1, T, F), dtype=torch.complex64).pin_memory()
+    for _ in range(2):
+        pipe.process(pcm, out)
+    torch.cuda.synchronize()
+    rep = pipe.report()
+    assert rep["slices"] == 2 and rep["crnn_ms_per_slice"] > 0
+    yq = (pcm.to(torch.float32) / 32768.0).to(dev)                      # what soundfile would hand the reference
+    Yref = ops.stft(yq[:, 0, 0].contiguous())
+    mz = torch.stack([dnn_mask.estimate_mask(pipe.models[0], Yref[b].T, None, device=dev) for b in range(B)])[:, None]
+    mw = torch.stack([dnn_mask.estimate_mask(pipe.models[1], Yref[b].T, None, device=dev) for b in range(B)])[:, None]
+    ref = tango_batched(yq, masks=(mz.contiguous(), mw.contiguous()), out_layout="TF", diagnostics=False)
+    for b in range(B):
+        assert rel_l2_mag(out[b, 0].numpy(), ref["yf"][b, 0].cpu().numpy()) < 1e-4     # untrained masks: degenerate GEVD
+    assert np.all(np.isfinite(out.numpy().view(np.float32)))
+
+
 def test_time_domain_outputs(dev):
     """post.to_time: one batched iSTFT for all outputs == librosa-style iSTFT of each (oracle); SI-SDR on the
     device == SI-SDR of the float64 oracle pipeline's output."""
