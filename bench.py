@@ -619,10 +619,11 @@ def main():
         dom = max(kernels, key=lambda k: k["us"])
         traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed ncu capture
         try:
+            norm = lambda t: t.replace("void", "").strip().split("<")[0].split("(")[0]      # kernel base name
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            ent = tj.get(args.workload, {})
-            if ent.get("batch") == B and ent.get("kernel") == dom["kernel"]:
-                traffic = ent["dram_bytes_per_launch"]
+            for ent in tj.values():
+                if ent.get("workload") == args.workload and not args.batch and norm(ent["kernel"]) == norm(dom["kernel"]):
+                    traffic = ent["dram_bytes_per_launch"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -9,18 +9,19 @@
 #include "common.cuh"
 #include "kernels.h"
 
-// tuning knobs (scripts/build_variants.py builds alternatives for A/B runs; the defaults are the measured best)
+// tuning knobs (scripts/build_variants.py builds alternatives for A/B runs; the defaults are the measured best:
+// profiles/ab_r2.md -- 123.6 us with UF 2 / WANT 4 / plain stores, 105.6 with streaming stores, 107.8 with WANT 32)
 #ifndef DISCO_FD_UF
-#define DISCO_FD_UF 2          // frames per thread and register buffer (frame-major output)
+#define DISCO_FD_UF 4          // frames per thread and register buffer (frame-major output)
 #endif
 #ifndef DISCO_FD_MINB
 #define DISCO_FD_MINB 2        // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef DISCO_FD_WANT
-#define DISCO_FD_WANT 4        // CTAs per SM the time split aims for (equal-sized CTAs: more waves, shorter tail)
+#define DISCO_FD_WANT 32       // CTAs per SM the time split aims for (equal-sized CTAs: more waves, shorter tail)
 #endif
 #ifndef DISCO_FD_STCS
-#define DISCO_FD_STCS 0        // 1: streaming (evict-first) stores for the three outputs
+#define DISCO_FD_STCS 1        // 1: streaming (evict-first) stores for the three outputs
 #endif
 
 namespace disco {

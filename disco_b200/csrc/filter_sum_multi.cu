@@ -42,6 +42,15 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
         const float2 v = a.W[((size_t)(b * K + i / D) * F + lg.fcol) * D + i % D];
         ws[i * 32 + lane] = a.conj_w ? cconj(v) : v;
     }
+    // NW % K == 0: a warp always serves the same node (item % K == warp % K), so its D taps live in registers
+    // for the whole pass instead of being re-read from shared memory for every frame (half of the LDS traffic)
+    constexpr bool WREG = (NW % K == 0);
+    float2 wr[WREG ? D : 1];
+    if (WREG) {
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; ++d) wr[d] = ws[((warp % K) * D + d) * 32 + lane];
+    }
     const float2* const Yb = a.in.Y + (size_t)b * K * C * T * F + lg.fcol;
     const float2* const Zb = a.in.Z + (size_t)b * K * T * F + lg.fcol;
     const size_t plane = (size_t)T * F;
@@ -78,19 +87,19 @@ __global__ void __launch_bounds__(256) filter_sum_multi_kernel(FilterArgs a) {
                 const int k = item % K, ts = item / K;
                 const float2* wk = ws + k * D * 32 + lane;
                 const float2* yk = xs + (k * C * TS + ts) * 32;
-                float2 acc = cfma(wk[0], yk[0], make_float2(0.f, 0.f));
+                float2 acc = cfma(WREG ? wr[0] : wk[0], yk[0], make_float2(0.f, 0.f));
                 float2 xr = yk[0];
 #pragma unroll
                 for (int c = 1; c < C; ++c) {
                     const float2 x = yk[c * TS * 32];
-                    acc = cfma(wk[c * 32], x, acc);
+                    acc = cfma(WREG ? wr[c] : wk[c * 32], x, acc);
                     if (c == a.ref) xr = x;
                 }
 #pragma unroll
                 for (int r = 0; r < K - 1; ++r) {      // reference order: nodes < k, then nodes > k
                     const int j = r + (r >= k ? 1 : 0);
                     const float2 x = xs[((K * C + j) * TS + ts) * 32];
-                    acc = cfma(wk[(C + r) * 32], x, acc);
+                    acc = cfma(WREG ? wr[C + r] : wk[(C + r) * 32], x, acc);
                     if (C + r == a.ref) xr = x;
                 }
                 const int t = (tile0 + i) * tspan + lg.tl + ts * lg.tmul;

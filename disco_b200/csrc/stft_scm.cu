@@ -44,25 +44,39 @@
 #ifndef DISCO_SS_FW
 #define DISCO_SS_FW 8          // FFT warps for up to 4 microphones (8 jobs per tile: 8 or 4)
 #endif
+#ifndef DISCO_SS_FG
+#define DISCO_SS_FG 1          // FFT warp groups working on alternate (smaller) tiles; 2 * FG pipeline stages
+#endif
+#ifndef DISCO_SS_FFTHI
+#define DISCO_SS_FFTHI 0       // 1: FFT warps get the highest warp indices (issue priority), SCM warps the lower ones
+#endif
 
 namespace disco {
 
-template <int N, int C>
+template <int N, int C, int NM = 1>
 struct StftCfg {
     static constexpr int RA = N / 32;              // radix of the per-lane first pass
     static constexpr int NB = 32 / RA;             // transforms per warp job
     static constexpr int HALF = N / 2;             // hop (50 % overlap)
     static constexpr int F = N / 2 + 1;            // bins
-    static constexpr int JOBS = 8;                 // jobs per tile
+    static constexpr bool WIDE = C > 4;            // 128 accumulators per bin
+    // FFT warp groups: group g transforms tiles it = g (mod FG); the tile shrinks with FG so that the shared-memory
+    // budget is unchanged while the pipeline gets 2 * FG stages (deeper input prefetch, finer hand-over to the SCM warps)
+    static constexpr int FG = (!WIDE && N == 512) ? DISCO_SS_FG : 1;
+    static constexpr int NSTG = 2 * FG;            // pipeline stages (samples and spectra)
+    static constexpr int JOBS = 8 / FG;            // jobs per tile
     static constexpr int ITEMS = JOBS * NB;        // (frame, channel-pair) transforms per tile
     static constexpr int P = (C + 1) / 2;          // channel pairs per frame
     static constexpr int TT = ITEMS / P;           // frames per tile
-    static constexpr bool WIDE = C > 4;            // 128 accumulators per bin
     // Roles on warpgroup boundaries + setmaxnreg: the SCM warps of wide arrays (128 accumulators) and of
     // two-mask runs (64) need more registers than an even split of the register file gives them.
     static constexpr bool REALLOC = (N == 512) || (WIDE && N == 256);
-    static constexpr int FFT_WARPS = (WIDE && N == 512) ? 4 : (WIDE ? 8 : DISCO_SS_FW);
-    static constexpr int JPW = JOBS / FFT_WARPS;   // jobs per FFT warp and tile
+    // measured (profiles/ab_r2.md): with two masks the SCM warps carry as much work as the FFT warps and four FFT
+    // warps running two jobs each per tile beat eight (143 vs 158 us at 64 x 4 mics x 10 s): fewer warps contend
+    // for the issue slots and the SCM warps get 152 registers
+    static constexpr int FFT_WARPS = (WIDE && N == 512) ? 4 : (WIDE ? 8 : ((NM == 2 && N == 512) ? 4 : DISCO_SS_FW));
+    static constexpr int FWG = FFT_WARPS / FG;     // FFT warps per group
+    static constexpr int JPW = JOBS / FWG;         // jobs per FFT warp and tile
     static constexpr int ROWP = 1056 / NB;         // spectrum row pitch (complex): a job = 32 x 33 scratch
     static constexpr int SCM_WARPS = N / 64;       // bins 0 .. N/2-1, one per thread
     static constexpr int LEAD_WARPS = REALLOC ? 4 : 1;   // warp 0 = loader; 1..3 idle (warpgroup padding)
@@ -72,18 +86,21 @@ struct StftCfg {
     static constexpr int SAMP = C * (TT + 1) * HALF;   // floats per sample stage
     // registers per thread at launch: each of the 4 SM sub-partitions holds 16384 registers and ceil(WARPS/4) warps
     static constexpr int REG_LAUNCH = 16384 / ((WARPS + 3) / 4) / 32 / 8 * 8;
-    static constexpr int REG_LEAD = 40, REG_FFT = 96, REG_SCM = WIDE ? 184 : 120;   // REALLOC only
+    static constexpr int REG_LEAD = 40, REG_FFT = 96, REG_SCM = WIDE ? 184 : (FFT_WARPS == 4 ? 152 : 120);   // REALLOC only
     static constexpr int REG_SUM = 128 * REG_LEAD + 32 * FFT_WARPS * REG_FFT + 32 * SCM_WARPS * REG_SCM;
     static_assert(!REALLOC || REG_SUM <= (REG_LAUNCH > 255 ? 255 : REG_LAUNCH) * THREADS,
                   "register budgets exceed the CTA's allocation");
 };
 
-int stft_tile_frames(int n_fft, int C) { return (8 * (32 / (n_fft / 32))) / ((C + 1) / 2); }
+int stft_tile_frames(int n_fft, int C) {
+    const int fg = (C <= 4 && n_fft == 512) ? DISCO_SS_FG : 1;
+    return ((8 / fg) * (32 / (n_fft / 32))) / ((C + 1) / 2);
+}
 
 template <int N, int C>
 __host__ __device__ inline size_t smem_bytes() {
     using G = StftCfg<N, C>;
-    return 2 * (size_t)G::SPEC * sizeof(float2) + 2 * (size_t)G::SAMP * sizeof(float) + (size_t)N * sizeof(float2) + 128 +
+    return G::NSTG * ((size_t)G::SPEC * sizeof(float2) + (size_t)G::SAMP * sizeof(float)) + (size_t)N * sizeof(float2) + 256 +
            64 * sizeof(float);
 }
 
@@ -177,26 +194,29 @@ struct ScmAcc {
 };
 
 template <int N, int C, int NM>
-__global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(StftArgs p) {
-    using G = StftCfg<N, C>;
+__global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel(StftArgs p) {
+    using G = StftCfg<N, C, NM>;
     constexpr int RA = G::RA, NB = G::NB, H = G::HALF, F = G::F, ROWP = G::ROWP, P = G::P, TT = G::TT;
     constexpr int SAMP = G::SAMP;
     constexpr int NACC = NM * 2 * C * C;
     constexpr int NMX = NM > 0 ? NM : 1;
     constexpr bool SCM = NM > 0;
-    constexpr int MC = (TT * NM <= 8) ? TT : ((8 / NMX) < TT ? (8 / NMX) : TT);   // frames per mask chunk
+    constexpr int MCAP = (G::REALLOC && G::REG_SCM >= 152 && !G::WIDE) ? 16 : 8;     // mask values in flight per thread
+    constexpr int MC = (TT * NM <= MCAP) ? TT : ((MCAP / NMX) < TT ? (MCAP / NMX) : TT);   // frames per mask chunk
     constexpr int NCH = (TT + MC - 1) / MC;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* spec = reinterpret_cast<float2*>(smem_raw);                  // [2][ITEMS][ROWP]
-    float* samp = reinterpret_cast<float*>(spec + 2 * G::SPEC);          // [2][C][(TT+1)*H]
-    float2* tw = reinterpret_cast<float2*>(samp + 2 * SAMP);             // [RA][32]
+    constexpr int NSTG = G::NSTG;
+    float2* spec = reinterpret_cast<float2*>(smem_raw);                  // [NSTG][ITEMS][ROWP]
+    float* samp = reinterpret_cast<float*>(spec + NSTG * G::SPEC);       // [NSTG][C][(TT+1)*H]
+    float2* tw = reinterpret_cast<float2*>(samp + NSTG * SAMP);          // [RA][32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw + N);
-    uint64_t* samp_full = bars;        // [2]  loader -> FFT   (1 arrival + TMA bytes)
-    uint64_t* samp_empty = bars + 2;   // [2]  FFT -> loader   (FFT_WARPS arrivals)
-    uint64_t* spec_full = bars + 4;    // [2]  FFT -> SCM      (FFT_WARPS arrivals)
-    uint64_t* spec_empty = bars + 6;   // [2]  SCM -> FFT      (SCM_WARPS + 1 arrivals)
-    float* nyq = reinterpret_cast<float*>(bars + 16);   // [TT * C <= 64] Nyquist-bin values of the current tile
+    uint64_t* samp_full = bars;               // [NSTG]  loader -> FFT   (1 arrival + TMA bytes)
+    uint64_t* samp_empty = bars + NSTG;       // [NSTG]  FFT -> loader   (FWG arrivals)
+    uint64_t* spec_full = bars + 2 * NSTG;    // [NSTG]  FFT -> SCM      (FWG arrivals)
+    uint64_t* spec_empty = bars + 3 * NSTG;   // [NSTG]  SCM -> FFT      (SCM_WARPS + 1 arrivals)
+    float* nyq = reinterpret_cast<float*>(bars + 32);   // [TT * C <= 64] Nyquist-bin values of the current tile
+    static_assert(4 * NSTG <= 32, "barrier area");
     static_assert(TT * C <= 64 && TT <= 32, "Nyquist staging");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -209,10 +229,10 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
 
     for (int i = tid; i < N; i += blockDim.x) tw[i] = p.twiddle[i];
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSTG; ++s) {
             mbar_init(&samp_full[s], 1);
-            mbar_init(&samp_empty[s], G::FFT_WARPS);
-            mbar_init(&spec_full[s], G::FFT_WARPS);
+            mbar_init(&samp_empty[s], G::FWG);
+            mbar_init(&spec_full[s], G::FWG);
             mbar_init(&spec_empty[s], G::SCM_WARPS + 1);
         }
         fence_mbar_init();
@@ -232,6 +252,11 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
         return p.mask_ft ? m[((size_t)grp * F + f) * T + t] : m[((size_t)grp * T + t) * F + f];
     };
 
+    // role layout: lead warp(s) first; then FFT and SCM warps in the order DISCO_SS_FFTHI selects (the warp
+    // scheduler favours higher warp indices among ready warps, and the FFT warps are the critical path)
+    constexpr int FFT_WARP0 = G::LEAD_WARPS + (DISCO_SS_FFTHI ? G::SCM_WARPS : 0);
+    constexpr int SCM_WARP0 = G::LEAD_WARPS + (DISCO_SS_FFTHI ? 0 : G::FFT_WARPS);
+    const bool is_fft = warp >= FFT_WARP0 && warp < FFT_WARP0 + G::FFT_WARPS;
     if (warp < G::LEAD_WARPS) {
         if (G::REALLOC) set_maxnreg<G::REG_LEAD, G::REG_LAUNCH>();
         if (warp != 0) return;
@@ -239,8 +264,8 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
         auto load_tile = [&](int it) {
             int grp, t0;
             tile_of(it, grp, t0);
-            const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
-            mbar_wait(&samp_empty[s], ((it >> 1) & 1) ^ 1);
+            const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
+            mbar_wait(&samp_empty[s], ((it / NSTG) & 1) ^ 1);
             const float* xg = p.x + (size_t)grp * C * L;
             float* dst = samp + s * SAMP;
             const int s0 = t0 * H - H;
@@ -304,19 +329,20 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
         };
         nyq_reset();
         if (DISCO_SS_PF > 0) {
-            for (int i = 1; i <= DISCO_SS_PF; ++i) prefetch_tile(i);
+            for (int i = NSTG - 1; i < NSTG - 1 + DISCO_SS_PF; ++i) prefetch_tile(i);
         }
-        load_tile(0);
+        for (int i = 0; i < NSTG - 1; ++i)
+            if (i < n_it) load_tile(i);
         for (int it = 0; it < n_it; ++it) {
-            if (DISCO_SS_PF > 0) prefetch_tile(it + 1 + DISCO_SS_PF);
-            if (it + 1 < n_it) load_tile(it + 1);
+            if (DISCO_SS_PF > 0) prefetch_tile(it + NSTG - 1 + DISCO_SS_PF);
+            if (it + NSTG - 1 < n_it) load_tile(it + NSTG - 1);
             int grp, t0;
             tile_of(it, grp, t0);
-            const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
+            const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             float mq[NMX];
 #pragma unroll
             for (int q = 0; q < NMX; ++q) mq[q] = (SCM && lane < nfr) ? mask_at(q, grp, t0 + lane, F - 1) : 0.f;
-            mbar_wait(&spec_full[s], (it >> 1) & 1);
+            mbar_wait(&spec_full[s], (it / NSTG) & 1);
 #pragma unroll
             for (int r = lane; r < TT * C; r += 32) {
                 const int tl_l = r / C, c_l = r % C;
@@ -375,21 +401,21 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
             }
             __syncwarp();   // nyq[] is rewritten by the next tile
         }
-    } else if (warp < G::LEAD_WARPS + G::FFT_WARPS) {
+    } else if (is_fft) {
         if (G::REALLOC) set_maxnreg<G::REG_FFT, G::REG_LAUNCH>();
         // =========================================================== FFT warps
-        const int w = warp - G::LEAD_WARPS;
+        const int wf = warp - FFT_WARP0, fgrp = wf / G::FWG, w = wf % G::FWG;   // group, index within the group
         constexpr bool WINREG = (RA <= 16);
         float win[WINREG ? RA : 1];   // window for n = lane + 32 j (pre-scaled by 1/2 for the two-for-one split)
         if (WINREG) {
 #pragma unroll
             for (int j = 0; j < RA; ++j) win[j] = p.window[lane + 32 * j];
         }
-        for (int it = 0; it < n_it; ++it) {
+        for (int it = fgrp; it < n_it; it += G::FG) {
             int grp, t0;
             tile_of(it, grp, t0);
-            const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
-            const uint32_t ph = (it >> 1) & 1;
+            const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
+            const uint32_t ph = (it / NSTG) & 1;
             const float* sm = samp + s * SAMP;
             mbar_wait(&samp_full[s], ph);
             {
@@ -401,10 +427,10 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
                 if (n_fill > 0) {   // CTA-uniform: cooperative scalar fill (reflect padding) by the FFT warps
                     const float* xg = p.x + (size_t)grp * C * L;
                     float* dst = samp + s * SAMP;
-                    named_bar_sync(1, 32 * G::FFT_WARPS);     // every FFT warp is done with this stage
+                    named_bar_sync(1 + fgrp, 32 * G::FWG);        // every FFT warp of the group is done with this stage
                     for (int c = 0; c < c_valid; ++c)
 #pragma unroll 4
-                        for (int q = w * 32 + lane; q < n_fill; q += 32 * G::FFT_WARPS) {
+                        for (int q = w * 32 + lane; q < n_fill; q += 32 * G::FWG) {
                             const int k = q < k_lo ? q : q + (k_hi - k_lo);
                             int sidx = s0 + k;               // librosa center=True, pad_mode='reflect'
                             if (sidx < 0) sidx = -sidx;
@@ -413,7 +439,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
                             if (sidx >= 0 && sidx < L) v = xg[(size_t)c * L + sidx];
                             dst[c * (TT + 1) * H + k] = v;
                         }
-                    named_bar_sync(1, 32 * G::FFT_WARPS);
+                    named_bar_sync(1 + fgrp, 32 * G::FWG);
                 }
             }
             mbar_wait(&spec_empty[s], ph ^ 1);                // spectrum stage s free (tile it-2 consumed)
@@ -481,22 +507,26 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
     } else {
         if (G::REALLOC) set_maxnreg<G::REG_SCM, G::REG_LAUNCH>();
         // =========================================================== SCM warps: thread <-> bin f
-        const int f = (warp - G::LEAD_WARPS - G::FFT_WARPS) * 32 + lane;   // 0 .. N/2 - 1
+        const int f = (warp - SCM_WARP0) * 32 + lane;   // 0 .. N/2 - 1
         const int fn = (N - f) & (N - 1);
         ScmAcc<C, NM> acc;
         float mk[NMX][MC];
-        // masks of chunk `ch` of tile `it` (a chunk past the CTA's last tile loads nothing)
+        // masks of chunk `ch` of tile `it` (a chunk past the CTA's last tile loads nothing): one base pointer per
+        // mask, frame stride hoisted (frame-major: F floats, (F, T) layout: 1)
+        const int m_st = p.mask_ft ? 1 : F;
+        const size_t m_f = p.mask_ft ? (size_t)f * T : (size_t)f;
         auto load_mask = [&](int it, int ch) {
             if (it >= n_it) return;
             int grp, t0;
             tile_of(it, grp, t0);
+            const size_t base = (size_t)grp * T * F + m_f + (size_t)(t0 + ch * MC) * m_st;
 #pragma unroll
-            for (int q = 0; q < NM; ++q)
+            for (int q = 0; q < NM; ++q) {
+                const float* mb = (q == 0 ? p.mask : p.mask2) + base;
 #pragma unroll
-                for (int i = 0; i < MC; ++i) {
-                    const int t = t0 + ch * MC + i;
-                    mk[q][i] = (ch * MC + i < TT && t < T) ? mask_at(q, grp, t, f) : 0.f;
-                }
+                for (int i = 0; i < MC; ++i)
+                    mk[q][i] = (ch * MC + i < TT && t0 + ch * MC + i < T) ? mb[i * m_st] : 0.f;
+            }
         };
         if (SCM) {
             acc.reset();
@@ -505,7 +535,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
         for (int it = 0; it < n_it; ++it) {
             int grp, t0;
             tile_of(it, grp, t0);
-            const int nfr = min(TT, T - t0), s = it & 1, c_valid = min(C, p.n_sig - grp * C);
+            const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             const float2* stage = spec + s * G::SPEC;
             float2* ybase = p.Y + ((size_t)grp * C * T + t0) * F + f;
             const size_t cstride = (size_t)T * F;
@@ -523,7 +553,7 @@ __global__ void __launch_bounds__(StftCfg<N, C>::THREADS, 1) stft_scm_kernel(Stf
                     else
                         load_mask(it + 1, 0);
                 }
-                if (ch == 0) mbar_wait(&spec_full[s], (it >> 1) & 1);
+                if (ch == 0) mbar_wait(&spec_full[s], (it / NSTG) & 1);
 #pragma unroll
                 for (int i = 0; i < MC; ++i) {
                     const int tl = ch * MC + i;
@@ -628,7 +658,7 @@ bool stft_scm_supported(int n_fft, int C, int n_mask) {
 
 template <int N, int C, int NM>
 static cudaError_t launch_one(const StftArgs& a, int n_cta, cudaStream_t st) {
-    using G = StftCfg<N, C>;
+    using G = StftCfg<N, C, NM>;
     auto kern = stft_scm_kernel<N, C, NM>;
     const size_t smem = smem_bytes<N, C>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -137,7 +137,7 @@ def concatenate_signals(y, z, k, m=1):
 # --------------------------------------------------------------------------- Tango
 def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512, n_hop=256,
                   mu=1, filter_type="gevd", rank=1, ref_mic=0, granularity="frame",
-                  masks=None):
+                  masks=None, double=False):
     """tango.py:252-457 with oracle masks (mods=None) and ref_mics = 0.
 
     y, s, n: [node][channel] 1-D float32 signals.  ``masks`` optionally overrides the
@@ -147,11 +147,18 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
     Deployment mode (``s is None``: no clean components exist, masks must be given, mask_for_z='local'): the
     STFTs of s and n and the diagnostic outputs sf, nf, z_s, z_n -- which the reference only computes because
     its evaluation script has the clean signals -- are skipped (those lists come back as None).
+    double=True evaluates the SAME algorithm in double precision (complex128 spectra, SCMs and LAPACK zggev):
+    the float64 yardstick for the modes oracle/tango_f64.py does not restate (ragged arrays, 'compressed', ...).
     """
     K = len(y)
     F = n_fft // 2 + 1
 
+    cdt = "complex128" if double else "complex64"
+
     def spec(x):
+        if double:
+            return librosa_np.stft(np.asarray(x, dtype=np.float64), n_fft=n_fft, hop_length=n_hop, center=True,
+                                   dtype=np.complex128)
         return librosa_np.stft(np.asarray(x), n_fft=n_fft, hop_length=n_hop, center=True)
 
     Y = [np.array([spec(c) for c in y[k]]) for k in range(K)]              # :335
@@ -163,7 +170,7 @@ def offline_tango(y, s, n, vads=("irm1", "irm1"), mask_for_z="local", n_fft=512,
     T = Y[0].shape[-1]
 
     def two_outputs():
-        return [np.zeros((F, T), "complex64") for _ in range(K)]
+        return [np.zeros((F, T), cdt) for _ in range(K)]
 
     z_y, z_s, z_n = two_outputs(), two_outputs(), two_outputs()
     zn = [None] * K

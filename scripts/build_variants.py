@@ -27,6 +27,10 @@ VARIANTS = {
     "ss_pf2": ("stft_scm.cu", ["-DDISCO_SS_PF=2"]),
     "ss_pf4": ("stft_scm.cu", ["-DDISCO_SS_PF=4"]),
     "ss_fw4": ("stft_scm.cu", ["-DDISCO_SS_FW=4"]),
+    "ss_fg2": ("stft_scm.cu", ["-DDISCO_SS_FG=2"]),
+    "ss_ffthi": ("stft_scm.cu", ["-DDISCO_SS_FFTHI=1"]),
+    "ss_fg2_ffthi": ("stft_scm.cu", ["-DDISCO_SS_FG=2", "-DDISCO_SS_FFTHI=1"]),
+    "ss_fg2_pf2": ("stft_scm.cu", ["-DDISCO_SS_FG=2", "-DDISCO_SS_PF=2"]),
 }
 
 

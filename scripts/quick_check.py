@@ -63,8 +63,8 @@ def correctness():
             check(tag + " Y", rel(Y, Yr), 2e-6)
             check(tag + " Rss", rel(Rss, Rs), 3e-6)
             check(tag + " Rnn", rel(Rnn, Rn), 3e-6)
-            Y0 = ops.stft(x, n_fft)
-            check(tag + " stft==fused Y", rel(Y0, Y), 1e-12)
+            Y0 = ops.stft(x, n_fft)       # groups signals by 4: same two-for-one partner only when C is 4 or 8
+            check(tag + " stft vs fused Y", rel(Y0, Y), 1e-12 if C in (4, 8) else 5e-7)
             if ops.stft_scm_supported(n_fft, C, 2):
                 m2 = torch.rand((G, T, F), generator=g).to(dev)
                 Y2, ws = ops.stft_scm2(x, m, m2, n_fft)

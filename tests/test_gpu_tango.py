@@ -17,11 +17,16 @@ TOL = 1e-5     # == conftest.TOL
 
 
 def f64_truth(name, y, s, n, vads, mfz):
-    """float64 oracle with the reference's float32 masks; None where the oracle has no such mode."""
+    """float64 yardstick: oracle/tango_f64.py (Cholesky-whitened eigh) where it restates the mode, otherwise the
+    reference's own algorithm evaluated in double precision (oracle/tango_np.py double=True: complex128 spectra and
+    SCMs, LAPACK zggev).  None for VAD / binary masks (their float32 mask inputs are part of the fixture)."""
     from oracle import librosa_np, tango_f64, tango_np
-    chans = [len(c) for c in y]
-    if len(set(chans)) != 1 or mfz not in ("local", "distant") or any(v[:3] not in ("irm", "iam") for v in vads):
+    if any(v[:3] not in ("irm", "iam") for v in vads):
         return None
+    chans = [len(c) for c in y]
+    if len(set(chans)) != 1 or mfz not in ("local", "distant"):
+        res = tango_np.offline_tango(y, s, n, vads=vads, mask_for_z=mfz, granularity="bin", double=True)
+        return dict(zip(NAMES, res))
     K = len(y)
     S = [librosa_np.stft(np.asarray(s[k][0])) for k in range(K)]
     N = [librosa_np.stft(np.asarray(n[k][0])) for k in range(K)]
