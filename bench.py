@@ -446,6 +446,7 @@ def main():
     ap.add_argument("--masks", default="oracle", choices=["oracle", "crnn"],
                     help="e2e leg: masks uploaded from the host (oracle) or predicted on device by the reference CRNN")
     ap.add_argument("--crnn-exact", action="store_true", help="run the CRNN in IEEE float32 (default: TF32)")
+    ap.add_argument("--crnn-bf16", action="store_true", help="run the CRNN under bf16 autocast (throughput only)")
     args = ap.parse_args()
     B, K, C, L, n_fft, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -573,7 +574,7 @@ def main():
         yf_host = torch.empty((B, K, T, F), dtype=torch.complex64).pin_memory()
         if args.masks == "crnn" and K == 1:
             from disco_b200.plan import CrnnTangoPipeline
-            pipe = CrnnTangoPipeline(B, C, L, n_fft, args.e2e_chunks, dev, exact=args.crnn_exact)
+            pipe = CrnnTangoPipeline(B, C, L, n_fft, args.e2e_chunks, dev, exact=args.crnn_exact, bf16=args.crnn_bf16)
             y_i16 = pipe.to_pcm(y_host)
 
             def e2e_step():   # int16 PCM H2D -> CRNN masks on device -> the whole path -> D2H of yf

@@ -198,7 +198,7 @@ class CRNN(nn.Module):
         else:
             raise NotImplementedError("forward_batch predicts the 'mid' or the 'last' frame")
         win = feats.unfold(2, self.x_out, 1)                             # [B, C, n, f_out, x_out] (view)
-        out = torch.empty((B, n, self.ff.layers[-1].out_features), dtype=feats.dtype, device=feats.device)
+        out = torch.empty((B, n, self.ff.layers[-1].out_features), dtype=torch.float32, device=feats.device)
         per = max(1, chunk // max(1, n))
         for b0 in range(0, B, per):                                      # bound the unfolded copy
             w = win[b0:b0 + per].permute(0, 2, 1, 4, 3).contiguous()     # (b, n, C, x_out, f_out)

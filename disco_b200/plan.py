@@ -131,8 +131,10 @@ class CrnnTangoPipeline:
     Only the signals cross PCIe on the way in.  The batch is cut into `chunks` slices on separate streams so
     upload, mask estimation, beamforming and download of different slices overlap."""
 
-    def __init__(self, B, C, L, n_fft=512, chunks=4, device=None, models=None, exact=False, seed=0):
+    def __init__(self, B, C, L, n_fft=512, chunks=4, device=None, models=None, exact=False, seed=0, bf16=False):
         from . import dnn_mask
+        torch.backends.cudnn.benchmark = True      # static shapes: let cuDNN pick its convolution algorithms once
+        self.bf16 = bool(bf16) and not exact
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.B, self.C, self.L, self.n_fft, self.exact = B, C, L, n_fft, exact
         chunks = max(1, min(chunks, B))
@@ -146,7 +148,8 @@ class CrnnTangoPipeline:
         self.pcm = [torch.empty((hi - lo, 1, C, L), dtype=torch.int16, device=self.device) for lo, hi in self.splits]
         self.ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in self.splits]
         self.how = ("CrnnTangoPipeline: %d batch slices; per slice int16 H2D -> x/32768 -> STFT(ref mic) -> 2 CRNNs (%s) -> "
-                    "graph replay -> D2H" % (chunks, "IEEE fp32" if exact else "TF32 convolutions / matmuls"))
+                    "graph replay -> D2H" % (chunks, "IEEE fp32" if exact else ("bf16 autocast" if self.bf16 else
+                                                                                 "TF32 convolutions / matmuls")))
 
     @staticmethod
     def to_pcm(y_host):
@@ -166,8 +169,9 @@ class CrnnTangoPipeline:
                 torch.mul(self.pcm[i], 1.0 / 32768.0, out=plan.y)          # exact: a power of two
                 e[1].record(st)
                 Yref = ops.stft(plan.y[:, 0, 0].contiguous(), self.n_fft)  # [Bc, T, F]
-                plan.mask_z[:, 0] = dnn_mask.estimate_masks_batch(self.models[0], Yref, exact=self.exact)
-                plan.mask_w[:, 0] = dnn_mask.estimate_masks_batch(self.models[1], Yref, exact=self.exact)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
+                    plan.mask_z[:, 0] = dnn_mask.estimate_masks_batch(self.models[0], Yref, exact=self.exact)
+                    plan.mask_w[:, 0] = dnn_mask.estimate_masks_batch(self.models[1], Yref, exact=self.exact)
                 e[2].record(st)
                 plan.run()
                 e[3].record(st)
@@ -182,5 +186,5 @@ class CrnnTangoPipeline:
         bf = [e[2].elapsed_time(e[3]) for e in self.ev]
         return {"slices": len(self.ev), "upload_convert_ms_per_slice": sum(up) / len(up),
                 "crnn_ms_per_slice": sum(nn) / len(nn), "beamform_ms_per_slice": sum(bf) / len(bf),
-                "crnn_ms_per_batch": sum(nn), "precision": "ieee fp32" if self.exact else "tf32",
+                "crnn_ms_per_batch": sum(nn), "precision": "ieee fp32" if self.exact else ("bf16 autocast" if self.bf16 else "tf32"),
                 "models": "2 x reference CRNN (517,729 parameters each), random weights"}
