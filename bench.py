@@ -350,6 +350,8 @@ def main_nodes(args):
     dev = torch.device("cuda", local_rank)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner out of stdout (one JSON line)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ops.init(n_fft)
     chunks = args.chunks if args.chunks > 0 else 4
@@ -372,7 +374,8 @@ def main_nodes(args):
     stats = {}
 
     def step():
-        return tango_node_sharded(y, mz, mw, chunks=chunks, stats=stats, n_fft=n_fft, out_layout="TF")
+        return tango_node_sharded(y, mz, mw, chunks=chunks, stats=stats, n_fft=n_fft, out_layout="TF",
+                                  reserve_sms=None if args.reserve_sms < 0 else args.reserve_sms)
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
@@ -416,6 +419,7 @@ def main_nodes(args):
                                          "all-gathered over NCCL in %d batch chunks, gather(i) overlapped with step 1(i+1), "
                                          "node-major Z read in place by step 2" % (Kl, world, chunks),
                           "mode": "deployment: mixture + masks in, yf / z out", "execution": "eager launches (no CUDA graph)",
+                          "reserved_sms": "library default (16 while gathers are in flight)" if args.reserve_sms < 0 else args.reserve_sms,
                           "l2": "inputs larger than L2 (y %.0f MB, Y %.0f MB per GPU)" % (B * Kl * C * L * 4 / 1e6, B * Kl * C * T * F * 8 / 1e6)},
                "clocks": summarize_clocks(samples),
                "exchange": {"collective": "ncclAllGather (all_gather_into_tensor), %d per step" % chunks,
@@ -445,6 +449,7 @@ def main():
     ap.add_argument("--shard", default="utterances", choices=["utterances", "nodes"])
     ap.add_argument("--masks", default="oracle", choices=["oracle", "crnn"],
                     help="e2e leg: masks uploaded from the host (oracle) or predicted on device by the reference CRNN")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="--shard nodes: SMs left free for NCCL (-1 = library default)")
     ap.add_argument("--crnn-exact", action="store_true", help="run the CRNN in IEEE float32 (default: TF32)")
     ap.add_argument("--crnn-bf16", action="store_true", help="run the CRNN under bf16 autocast (throughput only)")
     args = ap.parse_args()
@@ -502,6 +507,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs (seeded): B distinct utterances; masks from the clean components on the device

@@ -21,6 +21,7 @@ SIGNATURES = {
     "disco_last_error": (ctypes.c_char_p, []),
     "disco_n_frames": (c_int, [c_int, c_int]),
     "disco_init": (c_int, [c_int]),
+    "disco_set_reserved_sms": (c_int, [c_int]),
     "disco_stft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "disco_stft_scm_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "disco_stft_scm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

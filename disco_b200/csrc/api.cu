@@ -100,11 +100,17 @@ int get_tables(int n_fft, Tables* out) {
 struct StftPlan {
     int n_cta, tiles_per_grp, slots_per_grp;
 };
+// SMs the persistent fused kernel leaves free (disco_set_reserved_sms): room for the CTAs of a concurrent NCCL
+// collective, which cannot co-reside with a 213 KB-shared-memory CTA
+int g_reserved_sms = 0;
+
 StftPlan plan_stft(int n_grp, int C, int T, int n_fft) {
     StftPlan pl;
     pl.tiles_per_grp = stft_tiles_per_grp(n_fft, C, T);
     const long long total = (long long)n_grp * pl.tiles_per_grp;
-    pl.n_cta = (int)(total < sm_count() ? total : sm_count());
+    int sms = sm_count() - g_reserved_sms;
+    if (sms < 1) sms = 1;
+    pl.n_cta = (int)(total < sms ? total : sms);
     pl.slots_per_grp = stft_slots_per_grp(n_grp, pl.tiles_per_grp, pl.n_cta);
     return pl;
 }
@@ -172,6 +178,12 @@ int disco_abi_version(void) { return DISCO_ABI_VERSION; }
 const char* disco_last_error(void) { return g_err.c_str(); }
 
 int disco_n_frames(int length, int n_fft) { return 1 + length / (n_fft / 2); }
+
+int disco_set_reserved_sms(int n) {
+    if (n < 0 || n > 64) return fail(DISCO_ERR_INVALID, "reserved SMs must be in 0..64");
+    g_reserved_sms = n;
+    return 0;
+}
 
 int disco_init(int n_fft) {
     if (!valid_nfft(n_fft)) return fail(DISCO_ERR_INVALID, "n_fft must be 256, 512 or 1024");

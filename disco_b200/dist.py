@@ -76,7 +76,7 @@ def _gpu_step2(Y, Z, mask_w, nodes, n_fft=512, mu=1.0, filter_type="gevd", rank=
 
 
 def tango_node_sharded(y_local, mask_z, mask_w=None, group=None, step1=_gpu_step1, step2=_gpu_step2, chunks=1,
-                       stats=None, **kw):
+                       stats=None, reserve_sms=None, **kw):
     """Two-step Tango with the array nodes sharded over the ranks of `group`.
 
     y_local [B, Kl, C, L] -- this rank's Kl = K / world nodes; mask_z / mask_w [B, Kl, T, F].
@@ -84,6 +84,8 @@ def tango_node_sharded(y_local, mask_z, mask_w=None, group=None, step1=_gpu_step
     kw: forwarded to step 1 / step 2, each receiving the keywords it accepts (n_fft, mu, filter_type, rank for
     both; ref_mic for step 1; out_layout for step 2).
     stats: optional dict, filled with the bytes this rank received and CUDA events around every gather.
+    reserve_sms: SMs kept free of the persistent fused STFT+SCM kernel while gathers are in flight (default 16 on
+    GPUs when chunks > 1, so that the NCCL kernels can run beside step 1 of the next chunk; 0 otherwise).
     Returns dict(yf [B, Kl, T, F], z_y [B, Kl, T, F], Z: list of node-major chunks [K, B_chunk, T, F])."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     B, Kl = y_local.shape[:2]
@@ -93,6 +95,11 @@ def tango_node_sharded(y_local, mask_z, mask_w=None, group=None, step1=_gpu_step
     kw1, kw2 = _filter_kw(step1, kw), _filter_kw(step2, kw)
     cuda = y_local.is_cuda
     chunks = max(1, min(int(chunks), B))
+    if reserve_sms is None:
+        reserve_sms = 16 if (cuda and chunks > 1 and world > 1) else 0
+    if cuda and step1 is _gpu_step1:
+        from . import ops
+        ops.set_reserved_sms(reserve_sms)
     cuts = [shard_range(B, i, chunks) for i in range(chunks)]
     comp = torch.cuda.current_stream(y_local.device) if cuda else None
     comm = torch.cuda.Stream(device=y_local.device) if cuda else None
@@ -126,6 +133,8 @@ def tango_node_sharded(y_local, mask_z, mask_w=None, group=None, step1=_gpu_step
             if cuda:
                 comp.wait_event(done[j])
             yfs[j] = step2(st1[j]["Y"], Zs[j], mask_w[lo:hi], nodes, **kw2)
+    if cuda and step1 is _gpu_step1 and reserve_sms:
+        ops.set_reserved_sms(0)
     if stats is not None:
         stats["gathers"] = timing
         stats["bytes_received_per_step"] = sum(t[2] for t in timing) if cuda else None

@@ -144,6 +144,11 @@ def mwf_solve_workspace(ws, G, C, L, n_fft=512, mu=1.0, type="gevd", rank=1, wan
     return (W, T1, Rss, Rnn) if want_scm else (W, T1)
 
 
+def set_reserved_sms(n):
+    """Leave n SMs free of the persistent fused STFT+SCM kernel (room for a concurrent NCCL collective)."""
+    _lib.check(_lib.load().disco_set_reserved_sms(int(n)))
+
+
 def stft_scm_supported(n_fft, C, n_mask=1):
     """Whether the fused STFT+SCM kernel covers (n_fft, channels per group, number of masks)."""
     return bool(_lib.load().disco_stft_scm_supported(int(n_fft), int(C), int(n_mask)))

@@ -74,6 +74,12 @@ DISCO_API int disco_n_frames(int length, int n_fft);
  * created on first use, which must not happen inside CUDA-graph capture). */
 DISCO_API int disco_init(int n_fft);
 
+/* Leave `n` SMs (0..64, default 0) free of the persistent fused STFT+SCM kernel, which otherwise occupies every SM
+ * with one 213 KB-shared-memory CTA: a collective running on another stream (the NCCL all-gather of the compressed
+ * signals, reference tango.py:379-386, in node-sharded runs) then finds SMs for its own CTAs and really overlaps.
+ * Process-wide; the workspace functions and the kernels of one batch must see the same value. */
+DISCO_API int disco_set_reserved_sms(int n);
+
 /* ---- STFT --------------------------------------------------------------------------------
  * Replaces lb.core.stft(x, n_fft, hop_length=n_fft/2, center=True) [pad_mode='reflect', periodic
  * Hann] at reference tango.py:335-337, get_z_signals.py:274-276, post_generator.py:121,
