@@ -350,8 +350,8 @@ def main_nodes(args):
     dev = torch.device("cuda", local_rank)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner out of stdout (one JSON line)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")             # keep NCCL's version banner out of stdout (one JSON line)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ops.init(n_fft)
     chunks = args.chunks if args.chunks > 0 else 4
@@ -373,12 +373,40 @@ def main_nodes(args):
 
     stats = {}
 
-    def step():
-        return tango_node_sharded(y, mz, mw, chunks=chunks, stats=stats, n_fft=n_fft, out_layout="TF",
+    def eager_step(st=stats):
+        return tango_node_sharded(y, mz, mw, chunks=chunks, stats=st, n_fft=n_fft, out_layout="TF",
                                   reserve_sms=None if args.reserve_sms < 0 else args.reserve_sms)
     for _ in range(max(3, args.warmup)):
-        step()
+        eager_step()
     barrier()
+    # optional: the whole step (compute kernels, stream forks / joins, NCCL gathers) as ONE CUDA graph -- the eager step
+    # costs ~10 Python-level launches per chunk, which is what limits fine chunking
+    graph, execution = None, "eager launches (no CUDA graph)"
+    if args.graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                eager_step(None)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = eager_step(None)
+            barrier()
+            for _ in range(3):
+                graph.replay()
+            barrier()
+            execution = "CUDA graph of the whole step (kernels + NCCL all-gathers)"
+        except Exception as exc:           # capture of collectives not possible here: stay eager, say so
+            graph, execution = None, "eager launches (CUDA-graph capture failed: %s)" % str(exc).splitlines()[0][:120]
+            barrier()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            eager_step()
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
     if rank == 0:
@@ -389,7 +417,7 @@ def main_nodes(args):
     e0.record()
     for _ in range(args.steps):
         step()
-        gathers.append(stats["gathers"])
+        gathers.append(stats["gathers"])           # (graph replay: the events of the last eager warm-up step)
     e1.record()
     barrier()
     stop.set()
@@ -418,7 +446,7 @@ def main_nodes(args):
                           "parallelism": "node-sharded: %d node(s) of every utterance per rank x %d ranks; compressed signals z "
                                          "all-gathered over NCCL in %d batch chunks, gather(i) overlapped with step 1(i+1), "
                                          "node-major Z read in place by step 2" % (Kl, world, chunks),
-                          "mode": "deployment: mixture + masks in, yf / z out", "execution": "eager launches (no CUDA graph)",
+                          "mode": "deployment: mixture + masks in, yf / z out", "execution": execution,
                           "reserved_sms": "library default (16 while gathers are in flight)" if args.reserve_sms < 0 else args.reserve_sms,
                           "l2": "inputs larger than L2 (y %.0f MB, Y %.0f MB per GPU)" % (B * Kl * C * L * 4 / 1e6, B * Kl * C * T * F * 8 / 1e6)},
                "clocks": summarize_clocks(samples),
@@ -427,7 +455,8 @@ def main_nodes(args):
                             "gather_gbs_per_rank": g_bytes / (float(gt.item()) / 1e3) / 1e9 if g_bytes else None,
                             "nvlink_reference_gbs": 770.0,
                             "note": "gather time is measured on the communication stream (CUDA events), max over ranks; it "
-                                    "overlaps step 1 of the next chunk"},
+                                    "overlaps step 1 of the next chunk" + ("; under the CUDA graph it is the figure of the last "
+                                    "eager warm-up step" if graph is not None else "")},
                "gpu_launches": None, "roofline": None}
         print(json.dumps(res))
     dist.destroy_process_group()
@@ -449,6 +478,7 @@ def main():
     ap.add_argument("--shard", default="utterances", choices=["utterances", "nodes"])
     ap.add_argument("--masks", default="oracle", choices=["oracle", "crnn"],
                     help="e2e leg: masks uploaded from the host (oracle) or predicted on device by the reference CRNN")
+    ap.add_argument("--graph", action="store_true", help="--shard nodes: capture the step (kernels + NCCL gathers) in a CUDA graph")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="--shard nodes: SMs left free for NCCL (-1 = library default)")
     ap.add_argument("--crnn-exact", action="store_true", help="run the CRNN in IEEE float32 (default: TF32)")
     ap.add_argument("--crnn-bf16", action="store_true", help="run the CRNN under bf16 autocast (throughput only)")
@@ -507,8 +537,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner out of stdout (one JSON line)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")         # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs (seeded): B distinct utterances; masks from the clean components on the device

@@ -118,15 +118,17 @@ def tango_node_sharded(y_local, mask_z, mask_w=None, group=None, step1=_gpu_step
                 if cuda:
                     comm.wait_event(ready)
                     z_loc.record_stream(comm)
-                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    t0.record(comm)
+                    if stats is not None:                           # (no timing events inside a graph capture)
+                        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        t0.record(comm)
                 Zs[i] = all_gather_nodes(z_loc, group)              # the exchange step (NCCL over NVLink on GPUs)
                 if cuda:
-                    t1.record(comm)
+                    if stats is not None:
+                        t1.record(comm)
+                        timing.append((t0, t1, Zs[i].numel() * Zs[i].element_size() * (world - 1) // world))
                     done[i] = torch.cuda.Event()
                     done[i].record(comm)
                     Zs[i].record_stream(comp)
-                    timing.append((t0, t1, Zs[i].numel() * Zs[i].element_size() * (world - 1) // world))
         if i >= 1:
             j = i - 1
             lo, hi = cuts[j]

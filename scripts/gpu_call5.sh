@@ -17,7 +17,8 @@ case $N in
      timeout 400 $TR bench.py --gpus $N --workload cfg3 --shard nodes --steps 10 --warmup 3 --reserve-sms 0 > gpurun_out/c5_nodes_cfg3_n${N}_rs0.json 2> gpurun_out/c5_nodes_cfg3_n${N}_rs0.err
      timeout 400 $TR bench.py --gpus $N --workload cfg3 --shard nodes --steps 10 --warmup 3 --chunks 8 > gpurun_out/c5_nodes_cfg3_n${N}_chunks8.json 2> gpurun_out/c5_nodes_cfg3_n${N}_chunks8.err
      timeout 400 $TR bench.py --gpus $N --workload cfg3 --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/c5_bench_cfg3_n$N.json 2> gpurun_out/c5_bench_cfg3_n$N.err ;;
-  8) timeout 400 $TR bench.py --gpus $N --workload cfg5 --shard nodes --steps 10 --warmup 3 > gpurun_out/c5_nodes_cfg5_n$N.json 2> gpurun_out/c5_nodes_cfg5_n$N.err
-     timeout 400 $TR bench.py --gpus $N --workload cfg4_512 --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/c5_bench_cfg4_512_n$N.json 2> gpurun_out/c5_bench_cfg4_512_n$N.err ;;
+  8) timeout 400 $TR bench.py --gpus $N --workload cfg5 --shard nodes --steps 10 --warmup 3 --chunks 1 > gpurun_out/c5_nodes_cfg5_n${N}_chunks1.json 2> gpurun_out/c5_nodes_cfg5_n${N}_chunks1.err
+     timeout 400 $TR bench.py --gpus $N --workload cfg5 --shard nodes --steps 10 --warmup 3 --chunks 2 --graph > gpurun_out/c5_nodes_cfg5_n${N}_graph2.json 2> gpurun_out/c5_nodes_cfg5_n${N}_graph2.err
+     timeout 400 $TR bench.py --gpus $N --workload cfg5 --shard nodes --steps 10 --warmup 3 --chunks 4 --graph > gpurun_out/c5_nodes_cfg5_n${N}_graph4.json 2> gpurun_out/c5_nodes_cfg5_n${N}_graph4.err ;;
 esac
 ls -la gpurun_out | grep c5_ | head -20; for f in gpurun_out/c5_*n$N*.json; do head -c 400 $f; echo; done; tail -3 gpurun_out/c5_*n$N*.err 2>/dev/null | tail -20
