@@ -458,7 +458,14 @@ def main_nodes(args):
                                     "overlaps step 1 of the next chunk" + ("; under the CUDA graph it is the figure of the last "
                                     "eager warm-up step" if graph is not None else "")},
                "gpu_launches": None, "roofline": None}
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
+    if graph is not None:
+        # measured on 8 GPUs (round 2): tearing down the process group after a CUDA graph holding NCCL kernels was
+        # replayed hangs until the launcher's timeout; the line is out, every rank is past the last barrier -> leave
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     dist.destroy_process_group()
 
 
@@ -611,7 +618,8 @@ def main():
         yf_host = torch.empty((B, K, T, F), dtype=torch.complex64).pin_memory()
         if args.masks == "crnn" and K == 1:
             from disco_b200.plan import CrnnTangoPipeline
-            pipe = CrnnTangoPipeline(B, C, L, n_fft, args.e2e_chunks, dev, exact=args.crnn_exact, bf16=args.crnn_bf16)
+            pipe = CrnnTangoPipeline(B, C, L, n_fft, args.e2e_chunks, dev, exact=args.crnn_exact, bf16=args.crnn_bf16,
+                                     cudnn_benchmark=args.crnn_bf16)
             y_i16 = pipe.to_pcm(y_host)
 
             def e2e_step():   # int16 PCM H2D -> CRNN masks on device -> the whole path -> D2H of yf

@@ -244,21 +244,6 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
         grp = (int)(i / tiles_per_grp);
         t0 = (int)(i % tiles_per_grp) * TT;
     };
-    // tiles are walked in order: a cursor (group, tile index within the group) advances without divisions
-    struct TileCursor {
-        int grp, tix;
-    };
-    auto cur_init = [&](TileCursor& c, int it) {
-        int t0;
-        tile_of(it, c.grp, t0);
-        c.tix = t0 / TT;
-    };
-    auto cur_next = [&](TileCursor& c) {
-        if (++c.tix == tiles_per_grp) {
-            c.tix = 0;
-            ++c.grp;
-        }
-    };
     auto seg_slot = [&](int grp) {
         return blockIdx.x - cta_of_tile((long long)grp * tiles_per_grp, total, gridDim.x);
     };
@@ -276,8 +261,9 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
         if (G::REALLOC) set_maxnreg<G::REG_LEAD, G::REG_LAUNCH>();
         if (warp != 0) return;
         // =========================================================== LOADER (+ Nyquist bin)
-        auto load_tile = [&](int it, const TileCursor& tc) {
-            const int grp = tc.grp, t0 = tc.tix * TT;
+        auto load_tile = [&](int it) {
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             mbar_wait(&samp_empty[s], ((it / NSTG) & 1) ^ 1);
             const float* xg = p.x + (size_t)grp * C * L;
@@ -345,17 +331,13 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
         if (DISCO_SS_PF > 0) {
             for (int i = NSTG - 1; i < NSTG - 1 + DISCO_SS_PF; ++i) prefetch_tile(i);
         }
-        TileCursor ld, cu;                                // tile being loaded (NSTG - 1 ahead), tile being consumed
-        cur_init(ld, 0);
-        cu = ld;
-        for (int i = 0; i < NSTG - 1; ++i) {
-            if (i < n_it) load_tile(i, ld);
-            cur_next(ld);
-        }
-        for (int it = 0; it < n_it; ++it, cur_next(cu), cur_next(ld)) {
+        for (int i = 0; i < NSTG - 1; ++i)
+            if (i < n_it) load_tile(i);
+        for (int it = 0; it < n_it; ++it) {
             if (DISCO_SS_PF > 0) prefetch_tile(it + NSTG - 1 + DISCO_SS_PF);
-            if (it + NSTG - 1 < n_it) load_tile(it + NSTG - 1, ld);
-            const int grp = cu.grp, t0 = cu.tix * TT;
+            if (it + NSTG - 1 < n_it) load_tile(it + NSTG - 1);
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             float mq[NMX];
 #pragma unroll
@@ -394,7 +376,7 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
                         }
                     }
                 }
-                const bool seg_end = (it + 1 == n_it) || (cu.tix + 1 == tiles_per_grp);
+                const bool seg_end = (it + 1 == n_it) || ((lo + it + 1) % tiles_per_grp == 0);
                 if (seg_end) {
                     float* out = p.part + ((size_t)grp * p.slots_per_grp + seg_slot(grp)) * NACC * F + (F - 1);
 #pragma unroll
@@ -429,12 +411,9 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
 #pragma unroll
             for (int j = 0; j < RA; ++j) win[j] = p.window[lane + 32 * j];
         }
-        TileCursor cu;
-        cur_init(cu, fgrp < n_it ? fgrp : 0);
         for (int it = fgrp; it < n_it; it += G::FG) {
-            const int grp = cu.grp, t0 = cu.tix * TT;
-#pragma unroll
-            for (int u = 0; u < G::FG; ++u) cur_next(cu);
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             const uint32_t ph = (it / NSTG) & 1;
             const float* sm = samp + s * SAMP;
@@ -536,46 +515,26 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
         // mask, frame stride hoisted (frame-major: F floats, (F, T) layout: 1)
         const int m_st = p.mask_ft ? 1 : F;
         const size_t m_f = p.mask_ft ? (size_t)f * T : (size_t)f;
-        auto load_mask = [&](int it, const TileCursor& tc, int ch) {
+        auto load_mask = [&](int it, int ch) {
             if (it >= n_it) return;
-            const int grp = tc.grp, t0 = tc.tix * TT;
+            int grp, t0;
+            tile_of(it, grp, t0);
             const size_t base = (size_t)grp * T * F + m_f + (size_t)(t0 + ch * MC) * m_st;
-            const bool whole = (t0 + TT <= T);                // CTA-uniform: every frame of the tile exists
 #pragma unroll
             for (int q = 0; q < NM; ++q) {
                 const float* mb = (q == 0 ? p.mask : p.mask2) + base;
-                if (whole && !p.mask_ft) {                    // frame-major masks: immediate offsets, no predicates
 #pragma unroll
-                    for (int i = 0; i < MC; ++i)
-                        if (ch * MC + i < TT) mk[q][i] = mb[i * F];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < MC; ++i)
-                        mk[q][i] = (ch * MC + i < TT && t0 + ch * MC + i < T) ? mb[(size_t)i * m_st] : 0.f;
-                }
+                for (int i = 0; i < MC; ++i)
+                    mk[q][i] = (ch * MC + i < TT && t0 + ch * MC + i < T) ? mb[i * m_st] : 0.f;
             }
         };
-        TileCursor cu, nx;                                // this tile, the next one (mask prefetch)
-        cur_init(cu, 0);
-        nx = cu;
-        cur_next(nx);
         if (SCM) {
             acc.reset();
-            load_mask(0, cu, 0);
+            load_mask(0, 0);
         }
-        // one (frame, bin) point: un-mix the two-for-one spectra (window carries the 1/2)
-        //   A = Z[f] + conj(Z[N-f]),  B = -i (Z[f] - conj(Z[N-f]))
-        auto unmix = [&](const float2* stage, int tl, float2 (&y)[C]) {
-#pragma unroll
-            for (int pr = 0; pr < P; ++pr) {
-                const float2* row = stage + (size_t)(tl * P + pr) * ROWP;
-                const float2 zf = row[f], zn = row[fn];
-                y[2 * pr] = __fadd2_rn(zf, make_float2(zn.x, -zn.y));
-                if (2 * pr + 1 < C) y[2 * pr + 1] = __fadd2_rn(make_float2(zf.y, -zf.x), make_float2(zn.y, zn.x));
-            }
-        };
-        for (int it = 0; it < n_it; ++it, cur_next(cu), cur_next(nx)) {
-            const int grp = cu.grp, t0 = cu.tix * TT;
+        for (int it = 0; it < n_it; ++it) {
+            int grp, t0;
+            tile_of(it, grp, t0);
             const int nfr = min(TT, T - t0), s = it % NSTG, c_valid = min(C, p.n_sig - grp * C);
             const float2* stage = spec + s * G::SPEC;
             float2* ybase = p.Y + ((size_t)grp * C * T + t0) * F + f;
@@ -590,51 +549,40 @@ __global__ void __launch_bounds__(StftCfg<N, C, NM>::THREADS, 1) stft_scm_kernel
                     for (int i = 0; i < MC; ++i) mcur[q][i] = SCM ? mk[q][i] : 0.f;
                 if (SCM) {   // next chunk's masks: in flight while this chunk is processed
                     if (ch + 1 < NCH)
-                        load_mask(it, cu, ch + 1);
+                        load_mask(it, ch + 1);
                     else
-                        load_mask(it + 1, nx, 0);
+                        load_mask(it + 1, 0);
                 }
                 if (ch == 0) mbar_wait(&spec_full[s], (it / NSTG) & 1);
-                if (full) {                                   // full tile: straight-line code, no predicates
 #pragma unroll
-                    for (int i = 0; i < MC; ++i) {
-                        const int tl = ch * MC + i;
-                        if (tl < TT) {
-                            float2 y[C];
-                            unmix(stage, tl, y);
+                for (int i = 0; i < MC; ++i) {
+                    const int tl = ch * MC + i;
+                    if (tl < TT && (full || tl < nfr)) {
+                        // un-mix the two-for-one spectra (window carries the 1/2):
+                        //   A = Z[f] + conj(Z[N-f]),  B = -i (Z[f] - conj(Z[N-f]))
+                        float2 y[C];
 #pragma unroll
-                            for (int c = 0; c < C; ++c) __stcs(ybase + c * cstride + tl * F, y[c]);
-                            if (SCM) {
-                                float m[NMX];
-#pragma unroll
-                                for (int q = 0; q < NMX; ++q) m[q] = mcur[q][i];
-                                acc.step(y, m);
-                            }
+                        for (int pr = 0; pr < P; ++pr) {
+                            const float2* row = stage + (size_t)(tl * P + pr) * ROWP;
+                            const float2 zf = row[f], zn = row[fn];
+                            y[2 * pr] = __fadd2_rn(zf, make_float2(zn.x, -zn.y));
+                            if (2 * pr + 1 < C) y[2 * pr + 1] = __fadd2_rn(make_float2(zf.y, -zf.x), make_float2(zn.y, zn.x));
                         }
-                    }
-                } else {
 #pragma unroll
-                    for (int i = 0; i < MC; ++i) {
-                        const int tl = ch * MC + i;
-                        if (tl < TT && tl < nfr) {
-                            float2 y[C];
-                            unmix(stage, tl, y);
+                        for (int c = 0; c < C; ++c)
+                            if (full || c < c_valid) __stcs(ybase + c * cstride + tl * F, y[c]);
+                        if (SCM) {
+                            float m[NMX];
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
-                                if (c < c_valid) ybase[c * cstride + tl * F] = y[c];
-                            if (SCM) {
-                                float m[NMX];
-#pragma unroll
-                                for (int q = 0; q < NMX; ++q) m[q] = mcur[q][i];
-                                acc.step(y, m);
-                            }
+                            for (int q = 0; q < NMX; ++q) m[q] = mcur[q][i];
+                            acc.step(y, m);
                         }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&spec_empty[s]);
-            const bool seg_end = (it + 1 == n_it) || (cu.tix + 1 == tiles_per_grp);
+            const bool seg_end = (it + 1 == n_it) || ((lo + it + 1) % tiles_per_grp == 0);
             if (SCM && seg_end) {
                 acc.flush(p.part + ((size_t)grp * p.slots_per_grp + seg_slot(grp)) * NACC * F + f, F);
                 acc.reset();

@@ -70,14 +70,17 @@ class PostGenerator:
                               + "{}_{}.npy".format(str(rir), self.noise))
 
     def load_sigs(self, tar_list, noi_list):
-        """The loading half of mix_sigs (post_generator.py:99-118): float32 arrays [n_ch, L]; noise zero-padded /
-        cropped to the target length like `noi_seg[:len(noi)] += noi`."""
+        """The loading half of mix_sigs (post_generator.py:99-118): float32 arrays [n_ch, L]; noise zero-padded to
+        the target length like `noi_seg[:len(noi)] += noi`; a noise file LONGER than the target raises ValueError, as
+        that NumPy statement does in the reference."""
         tars = [wav_io.read(tar_list[ch], dtype="float32")[0] for ch in range(self.n_ch)]
         L = len(tars[0])
         nois = np.zeros((self.n_ch, L), dtype=np.float32)
         for ch in range(self.n_ch):
             noi = wav_io.read(noi_list[0][ch], dtype="float32")[0]
-            nois[ch, :len(noi)] = noi[:L]
+            if len(noi) > L:
+                raise ValueError("noise file %s has %d samples, more than the target's %d" % (noi_list[0][ch], len(noi), L))
+            nois[ch, :len(noi)] = noi
         return np.stack(tars), nois
 
     # ------------------------------------------------------------------ compute (device)

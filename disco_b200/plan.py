@@ -131,9 +131,11 @@ class CrnnTangoPipeline:
     Only the signals cross PCIe on the way in.  The batch is cut into `chunks` slices on separate streams so
     upload, mask estimation, beamforming and download of different slices overlap."""
 
-    def __init__(self, B, C, L, n_fft=512, chunks=4, device=None, models=None, exact=False, seed=0, bf16=False):
+    def __init__(self, B, C, L, n_fft=512, chunks=4, device=None, models=None, exact=False, seed=0, bf16=False,
+                 cudnn_benchmark=False):
         from . import dnn_mask
-        torch.backends.cudnn.benchmark = True      # static shapes: let cuDNN pick its convolution algorithms once
+        if cudnn_benchmark:                        # static shapes: let cuDNN pick its convolution algorithms once
+            torch.backends.cudnn.benchmark = True  # (process-wide switch, hence opt-in)
         self.bf16 = bool(bf16) and not exact
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.B, self.C, self.L, self.n_fft, self.exact = B, C, L, n_fft, exact

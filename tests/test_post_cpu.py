@@ -75,6 +75,11 @@ def test_post_generator_host_logic(tmp_path):
     assert [int(p.split("_Ch-")[-1].split(".wav")[0]) for p in tar] == list(range(1, 17))
     tars, nois = gen.load_sigs(tar, noi)
     assert tars.shape == (16, 2000) and nois.shape == (16, 2000) and tars.dtype == np.float32
+    from disco_b200 import wav_io
+    fs, long_noise = wav_io.read(noi[0][0], dtype="float32")[1], np.zeros(2001, dtype=np.float32)
+    wav_io.write(noi[0][0], long_noise, fs)
+    with pytest.raises(ValueError):                    # the reference's `noi_seg[:len(noi)] += noi` cannot broadcast
+        gen.load_sigs(tar, noi)
     assert PostGenerator(11, 1, "living", "fs", [0, 6], root, n_samples=[10, 4, 2], device="cpu").case == "val"
     with pytest.raises(AssertionError):
         PostGenerator(9, 3, "living", "fs", [0, 6], root, n_samples=[10, 2, 2], device="cpu")      # spans two sets
