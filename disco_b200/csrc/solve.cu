@@ -26,6 +26,11 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// 1: deal the entries of the Hermitian squaring to all G lanes of a group (see g_top_eigpair); experimental, off
+#ifndef DISCO_SOLVE_SPREAD
+#define DISCO_SOLVE_SPREAD 0
+#endif
+
 namespace disco {
 
 struct cd {
@@ -224,10 +229,65 @@ DISCO_DEV double g_top_eigpair(const cd* A, cd* B, int l, unsigned gm, cd* v_out
         for (int j = 0; j < D; ++j) B[l * P + j] = it * A[l * P + j];
     }
     __syncwarp(gm);
-    // B is Hermitian, so is B^2: lane l computes only the H = D/2 + 1 entries (l, (l + s) mod D), s = 0..D/2, of
-    // its row (every unordered pair has an owner; for even D the pairs at distance D/2 have two owners that
-    // compute and store the same numbers) and stores each with its conjugate mirror: ~half the D^3 complex MACs.
+    // B is Hermitian, so is B^2: only the NE = D (D + 1) / 2 entries (i <= j) are computed, each stored with its
+    // conjugate mirror.  Two ways of dealing them to the group's G lanes:
+    //  * SPREAD (-DDISCO_SOLVE_SPREAD=1; D = 5, 6, 9, 10, ...: G is well above D): entry e goes to lane e mod G, so
+    //    the lanes beyond D work too -- 3 entries per lane instead of 5 at D = 9.  Written at the end of round 2
+    //    and NOT yet run on a GPU, hence compiled out by default (the default build's SASS is unchanged);
+    //  * otherwise lane l owns the H = D/2 + 1 entries (l, (l + s) mod D) of its row (every unordered pair has an
+    //    owner; for even D the pairs at distance D/2 have two owners that compute and store the same numbers).
     constexpr int H = D / 2 + 1;
+    constexpr int NE = D * (D + 1) / 2, EPL = (NE + G - 1) / G;
+    constexpr bool SPREAD = DISCO_SOLVE_SPREAD && EPL < H;
+    if constexpr (SPREAD) {
+        int ei[EPL], ej[EPL];
+#pragma unroll
+        for (int s = 0; s < EPL; ++s) {
+            int e = l + s * G, i = 0;
+            if (e >= NE) {
+                ei[s] = -1;
+                ej[s] = 0;
+                continue;
+            }
+            while (e >= D - i) {
+                e -= D - i;
+                ++i;
+            }
+            ei[s] = i;
+            ej[s] = i + e;
+        }
+        for (int iter = 0; iter < 40; ++iter) {
+            cd c[EPL];
+            double fro = 0.0, dg = 0.0;
+#pragma unroll
+            for (int s = 0; s < EPL; ++s) {
+                c[s] = mk(0.0, 0.0);
+                if (ei[s] < 0) continue;
+                const cd *ri = B + ei[s] * P, *rj = B + ej[s] * P;      // B[k][j] = conj(B[j][k]): two row reads
+                for (int k = 0; k < D; ++k) c[s] = c[s] + ri[k] * conj(rj[k]);
+                if (ei[s] == ej[s]) {
+                    c[s].y = 0.0;
+                    dg += c[s].x;
+                    fro += c[s].x * c[s].x;
+                } else {
+                    fro += 2.0 * norm2(c[s]);
+                }
+            }
+            const double trc = gsum<G>(dg, gm);      // tr(B^2) = ||B||_F^2 of the previous iterate (<= 1)
+            const double fr2 = gsum<G>(fro, gm);     // ||B^2||_F^2
+            __syncwarp(gm);                          // everyone has finished reading B
+            const double it = 1.0 / trc;
+#pragma unroll
+            for (int s = 0; s < EPL; ++s) {
+                if (ei[s] < 0) continue;
+                const cd v = it * c[s];
+                B[ei[s] * P + ej[s]] = v;
+                if (ei[s] != ej[s]) B[ej[s] * P + ei[s]] = conj(v);
+            }
+            __syncwarp(gm);
+            if (1.0 - fr2 / (trc * trc) <= 1e-14) break;   // new iterate is rank one (group-uniform)
+        }
+    } else {
     int col[H];
 #pragma unroll
     for (int s = 0; s < H; ++s) col[s] = (l + s) % D;
@@ -266,6 +326,7 @@ DISCO_DEV double g_top_eigpair(const cd* A, cd* B, int l, unsigned gm, cd* v_out
         }
         __syncwarp(gm);
         if (1.0 - fr2 / (trc * trc) <= 1e-14) break;   // new iterate is rank one (group-uniform)
+    }
     }
     // B ~ v v^H: take the column with the largest diagonal, normalise
     int jm = 0;

@@ -31,6 +31,8 @@ VARIANTS = {
     "ss_ffthi": ("stft_scm.cu", ["-DDISCO_SS_FFTHI=1"]),
     "ss_fg2_ffthi": ("stft_scm.cu", ["-DDISCO_SS_FG=2", "-DDISCO_SS_FFTHI=1"]),
     "ss_fg2_pf2": ("stft_scm.cu", ["-DDISCO_SS_FG=2", "-DDISCO_SS_PF=2"]),
+    # written at the end of round 2, not yet run on a GPU: squaring entries dealt to all lanes of a solver group
+    "sv_spread": ("solve.cu", ["-DDISCO_SOLVE_SPREAD=1"]),
 }
 
 

@@ -33,6 +33,19 @@ __host__ __device__ inline float sample_m(int cta, int fr, int bin) {
 
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
+// volatile shared loads: the tile is re-read on every pass (ptxas otherwise hoists the loads AND the TF32 splits out
+// of the pass loop, leaving only HMMAs in it -- a real kernel sees new frames on every k-step)
+__device__ __forceinline__ float2 lds_v2(const float2* p) {
+    float2 v;
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ float lds_v1(const float* p) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------ (A) packed FP32
 // out[cta][set][bin][i][j] (i <= j), complex
 __global__ void __launch_bounds__(THREADS, 1) scm_ffma2(float2* __restrict__ out, int rep) {
@@ -51,15 +64,14 @@ __global__ void __launch_bounds__(THREADS, 1) scm_ffma2(float2* __restrict__ out
 #pragma unroll
     for (int i = 0; i < D * (D - 1) / 2; ++i) os[i] = on[i] = make_float2(0.f, 0.f);
     for (int r = 0; r < rep; ++r) {
-        asm volatile("" ::: "memory");
 #pragma unroll 1
         for (int fr = 0; fr < TT; ++fr) {
-            const float m = M[fr * BINS + bin];
+            const float m = lds_v1(M + fr * BINS + bin);
             const float2 mm = make_float2(m, 1.f - m);
             float2 x[D], xs[D], xn[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                x[c] = X[(c * TT + fr) * BINS + bin];
+                x[c] = lds_v2(X + (c * TT + fr) * BINS + bin);
                 xs[c] = __fmul2_rn(x[c], make_float2(m, m));
                 xn[c] = __fadd2_rn(x[c], make_float2(-xs[c].x, -xs[c].y));
                 const float p = fmaf(x[c].y, x[c].y, x[c].x * x[c].x);
@@ -126,12 +138,11 @@ __global__ void __launch_bounds__(THREADS, 1) scm_mma(float2* __restrict__ out, 
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[q][s][h][e] = 0.f;
         for (int r = 0; r < rep; ++r) {
-            asm volatile("" ::: "memory");
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
                 const int bin = warp * BPW + b0 + q;
-                const float2 x0 = X[bin * PITCH + g * TT + t], x1 = X[bin * PITCH + g * TT + t + 4];
-                const float m0 = M[bin * TT + t], m1 = M[bin * TT + t + 4];
+                const float2 x0 = lds_v2(X + bin * PITCH + g * TT + t), x1 = lds_v2(X + bin * PITCH + g * TT + t + 4);
+                const float m0 = lds_v1(M + bin * TT + t), m1 = lds_v1(M + bin * TT + t + 4);
                 // A = masked [re; im] (rows) x frames; B = frames x [re | im] (the same samples, unmasked)
                 float av[2][4];
                 av[0][0] = m0 * x0.x; av[0][1] = m0 * x0.y; av[0][2] = m1 * x1.x; av[0][3] = m1 * x1.y;
