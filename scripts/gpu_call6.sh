@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOT RUN in round 2: the 8-GPU call before it used up the round's GPU minutes (two bench processes hung in the NCCL
+# teardown after CUDA-graph replays until their timeouts; bench.py now leaves through os._exit in that mode).
 # Final single-GPU call of round 2: whole suite on the final kernels, bench lines of every BASELINE shape, CRNN e2e
 # variants, launch lists, ncu captures of the kernels that changed last (exported to CSV on the box)
 cd "$GRAFT_REPO_ROOT" || exit 1
