@@ -136,14 +136,36 @@ class CpuArm:
 
 
 # ----------------------------------------------------------------------------------------------
+def _nvml_handle(gpu_index):
+    import pynvml as nv
+    nv.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+    return nv, nv.nvmlDeviceGetHandleByIndex(phys)
+
+
+def bind_host_to_gpu(gpu_index):
+    """Multi-GPU runs: keep this rank's host threads -- and therefore the first touch of its pinned staging
+    buffers -- on the CPUs of the GPU's NUMA node (NVML's affinity mask).  Round 2 measured the host-to-host leg at
+    31 M frames/s on 8 GPUs against 8 x 8.2 M alone with unbound ranks (4 of the 8 GPUs hang off the other socket).
+    Any failure (no NVML, restricted cpuset) leaves the process as it was.  Returns the CPU count bound to, or None."""
+    try:
+        nv, h = _nvml_handle(gpu_index)
+        allowed = os.sched_getaffinity(0)
+        words = nv.nvmlDeviceGetCpuAffinity(h, max(allowed) // 64 + 1)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def clock_sampler(stop, out, gpu_index):
     """Sample SM clock and throttle reasons through NVML every ~2 ms while the timed region runs."""
     try:
-        import pynvml as nv
-        nv.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
-        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        nv, h = _nvml_handle(gpu_index)
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not stop.is_set():
@@ -546,6 +568,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        bound = bind_host_to_gpu(local_rank)     # before the pinned buffers are allocated
+        config["host_affinity"] = ("rank bound to the %d CPUs of its GPU's NUMA node" % bound) if bound else "unbound"
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")         # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)

@@ -35,3 +35,32 @@ def test_reference_arm_line_contract():
 def test_reference_arm_other_workload():
     d = _run("--workload", "cfg3")
     assert d["config"]["workload"].startswith("cfg3") and d["config"]["nodes"] == 4
+
+
+def test_numa_binding_helper_decodes_nvml_mask_and_survives_its_absence():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    before = os.sched_getaffinity(0)
+
+    def broken(_):
+        raise RuntimeError("no NVML")
+    b._nvml_handle = broken
+    assert b.bind_host_to_gpu(0) is None and os.sched_getaffinity(0) == before
+    first = min(before)
+
+    class FakeNvml:
+        @staticmethod
+        def nvmlDeviceGetCpuAffinity(handle, n_words):
+            words = [0] * n_words
+            words[first // 64] = 1 << (first % 64)
+            return words
+    b._nvml_handle = lambda i: (FakeNvml, None)
+    try:
+        if len(before) > 1:
+            assert b.bind_host_to_gpu(0) == 1 and os.sched_getaffinity(0) == {first}
+        else:
+            assert b.bind_host_to_gpu(0) is None          # mask == allowed set: nothing to do
+    finally:
+        os.sched_setaffinity(0, before)
